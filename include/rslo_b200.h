@@ -1,0 +1,134 @@
+/*
+ * rslo_b200.h — C ABI of the B200-native kernels behind RSLO's per-frame-pair hot path.
+ *
+ * The reference has exactly one native boundary on this path, the pybind module `cd`
+ * (thirdparty/chamfer_distance/chamfer_distance.cpp:237-244): caller-allocated contiguous
+ * float32 / int32 buffers, written in place, void return, errors printf'd, legacy default stream.
+ * Everything else the reference reaches through Python calls into the un-vendored spconv fork
+ * (rslo/builder/voxel_builder.py:48-54, rslo/models/middle.py:119-245).  This header keeps the
+ * `cd` calling convention (borrowed device pointers, no allocation inside, in-place outputs) and
+ * extends it to the other operators of the path, with three changes: every entry point takes the
+ * CUDA stream to run on, returns 0 or a cudaError_t value (text via rslo_last_error()), and scratch
+ * memory comes from a caller-provided workspace sized by the matching *_workspace_bytes().
+ *
+ * All pointers are DEVICE pointers unless the name ends in _host.  Row counts that depend on the
+ * data are passed twice: `n_cap` (rows allocated / grid size) and `n_dev` (device int holding the
+ * live count, or NULL meaning n_cap), so a frame can be enqueued without host round trips.
+ * No torch types appear here; the Python side (rslo_b200/_lib.py) binds this with ctypes.
+ */
+#ifndef RSLO_B200_H
+#define RSLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rslo_stream_t; /* cudaStream_t */
+
+int rslo_abi_version(void);
+const char* rslo_last_error(void);
+
+/* ---- a10: exact nearest neighbour ---------------------------------------------------------------
+ * Replaces cd.forward_cuda_one_direction (chamfer_distance.cpp:237-244 ->
+ * ChamferDistanceKernel, chamfer_distance.cu:6-137) for batch 1: for each of n query points the
+ * squared distance to, and index of, its nearest of m target points; bit-identical to the reference
+ * kernel's output (d = fma(z,z,fma(x,x,y*y)), lowest index wins ties).  Uniform-grid search with a
+ * conservative termination bound; queries that cannot be bounded fall back to an exhaustive scan. */
+size_t rslo_nn_workspace_bytes(int n, int m);
+int rslo_nn_exact(const float* query, int n, const float* target, int m, float* dist, int32_t* idx,
+                  void* workspace, size_t workspace_bytes, rslo_stream_t stream);
+/* Brute-force tiled variant (same results); kept as the in-library cross-check and for tiny m. */
+int rslo_nn_brute(const float* query, int n, const float* target, int m, float* dist, int32_t* idx,
+                  rslo_stream_t stream);
+
+/* ---- a1 + a3: voxeliser (+ fused VFE mean) ------------------------------------------------------
+ * Replaces spconv.utils.VoxelGenerator.generate as called through _VoxelGenerator.generate
+ * (rslo/builder/voxel_builder.py:48-54; call site rslo/data/preprocess.py:493) and, when `mean` is
+ * given, SimpleVoxel_XYZINormalC.forward (rslo/models/voxel_encoder.py:272-280).
+ * points [P,F] f32.  Outputs (rows in first-come order, exactly the sequential scan's):
+ *   voxels   [max_voxels,max_points,F] f32 zero padded, or NULL to skip materialising it;
+ *   coors    [max_voxels,coor_stride] i32, last three columns (z,y,x); with coor_stride 4 column 0
+ *            is set to batch_idx (merge_second_batch's pad, rslo/data/preprocess.py:84-85);
+ *   num_points [max_voxels] i32;  mean [max_voxels,7] f32 or NULL;
+ *   n_voxels_dev: device int, number of voxels produced;
+ *   cells / perm: optional (may be NULL) site table of the produced voxels over a
+ *            (table_d, gy, gx) cell grid for rslo_subm_table / rslo_strided_sites — cells is
+ *            2*ceil(table_d*gy*gx/32) uint32, perm is P int32.
+ * height_threshold < 0 keeps every voxel (the shipped configs: -1). */
+size_t rslo_voxelize_workspace_bytes(int P, int gx, int gy, int table_d, int max_voxels);
+int rslo_voxelize(const float* points, int P, int F, const float* voxel_size_host,
+                  const float* pc_range_host, int gx, int gy, int gz, int max_points, int max_voxels,
+                  int block_factor, int block_size, float height_threshold, int batch_idx,
+                  float* voxels, int32_t* coors, int coor_stride, int32_t* num_points, float* mean,
+                  int32_t* n_voxels_dev, uint32_t* cells, int32_t* perm, int table_d,
+                  void* workspace, size_t workspace_bytes, rslo_stream_t stream);
+
+/* VFE alone on materialised voxels (voxel_encoder.py:272-280). */
+int rslo_vfe_mean(const float* voxels, const int32_t* num_points, int n, int max_points, int F,
+                  float* mean, rslo_stream_t stream);
+
+/* ---- a5: sparse-conv index generation -----------------------------------------------------------
+ * Replaces spconv's get_indice_pairs behind SubMConv3d / SparseConv3d / SparseInverseConv3d
+ * (rslo/models/middle.py:119-213).  Tables are output-stationary: nbr[o*K+k] = input row or -1,
+ * K = kd*kh*kw, k row-major (kz,ky,kx).
+ * Site table of a level: cells = 2*ceil(D*H*W/32) uint32 ({bitmap word, rank of its first bit}),
+ * perm = rank -> row (NULL when rows are already in sorted cell order). */
+size_t rslo_site_table_workspace_bytes(int D, int H, int W);
+int rslo_site_table_build(const int32_t* coors, int coor_stride, int n_cap, const int32_t* n_dev,
+                          int D, int H, int W, uint32_t* cells, int32_t* perm, void* workspace,
+                          size_t workspace_bytes, rslo_stream_t stream);
+int rslo_subm_table(const int32_t* coors, int coor_stride, int n_cap, const int32_t* n_dev, int D,
+                    int H, int W, const uint32_t* cells, const int32_t* perm, int kd, int kh, int kw,
+                    int32_t* nbr, rslo_stream_t stream);
+/* Strided conv: output site set (sorted by cell index), its site table, and both tables.
+ * out_coors [out_cap,4] (b,z,y,x); nbr [out_cap,K]; nbr_inv [n_cap,K] (the SparseInverseConv3d
+ * table: nbr_inv[i*K+k] = o iff nbr[o*K+k] = i); n_out_dev device int. */
+size_t rslo_strided_workspace_bytes(int oD, int oH, int oW);
+int rslo_strided_table(const int32_t* coors, int coor_stride, int n_cap, const int32_t* n_dev,
+                       int D, int H, int W, int kd, int kh, int kw, int sd, int sh, int sw, int pd,
+                       int ph, int pw, uint32_t* out_cells, int32_t* out_coors, int out_cap,
+                       int32_t* n_out_dev, int32_t* nbr, int32_t* nbr_inv, void* workspace,
+                       size_t workspace_bytes, rslo_stream_t stream);
+
+/* ---- a6: sparse convolution ---------------------------------------------------------------------
+ * out[o,:] = act( scale * (bias + sum_k in[nbr[o,k],:] @ W[k]) + shift )
+ * Replaces Fsp.indice_conv / indice_inverse_conv + the LeakyReLU (and eval-mode BatchNorm1d of the
+ * covariance decoder) that follow each layer in middle.py:119-213.  W [K,Cin,Cout] f32 (the
+ * reference's [kD,kH,kW,Cin,Cout] state_dict layout), bias [Cout] or NULL, scale/shift [Cout] or
+ * NULL, act: 0 none, 1 LeakyReLU(slope). */
+int rslo_spconv_forward(const float* in, const int32_t* nbr, int n_out_cap, const int32_t* n_out_dev,
+                        int K, int Cin, int Cout, const float* weight, const float* bias,
+                        const float* scale, const float* shift, int act, float slope, float* out,
+                        rslo_stream_t stream);
+/* Wt[k] = W[k']^T ([K,Cout,Cin]), k' = K-1-k when mirror != 0 else k: the filter bank the data
+ * gradient convolves with. */
+int rslo_spconv_transpose_weight(const float* weight, int K, int Cin, int Cout, int mirror,
+                                 float* weight_t, rslo_stream_t stream);
+/* d(in)[i,:] = sum_k g[nbr_t[i,k],:] @ Wt[k] — the data gradient is itself a gather-convolution over
+ * the transposed table: nbr_inv for a strided conv, nbr for an inverse conv, and for a submanifold
+ * conv the same table with mirrored offsets (Wt built with mirror=1).  Cin/Cout are the FORWARD
+ * layer's; grad_out [n_out,Cout], grad_in [n_in,Cin]. */
+int rslo_spconv_backward_data(const float* grad_out, const int32_t* nbr_t, int n_in_cap,
+                              const int32_t* n_in_dev, int K, int Cin, int Cout, const float* weight_t,
+                              float* grad_in, rslo_stream_t stream);
+/* dW[k] += in[nbr[o,k],:]^T (x) g[o,:]  (dW must be zeroed by the caller), dbias[c] += sum_o g. */
+int rslo_spconv_backward_weight(const float* in, const float* grad_out, const int32_t* nbr,
+                                int n_out_cap, const int32_t* n_out_dev, int K, int Cin, int Cout,
+                                float* grad_weight, float* grad_bias, rslo_stream_t stream);
+
+/* ---- a7: SparseConvTensor.dense() + view (middle.py:240-243) ------------------------------------
+ * feat [n,C] at sites of a (D,H,W) level -> dense [C*D, H, W] f32 (zero where no site). */
+int rslo_dense_from_sites(const float* feat, int C, const uint32_t* cells, const int32_t* perm,
+                          int D, int H, int W, float* dense, rslo_stream_t stream);
+/* gradient of the above: grad_feat[r,c] = grad_dense[c, cell(r)] */
+int rslo_dense_backward(const float* grad_dense, int C, const int32_t* coors, int coor_stride,
+                        int n_cap, const int32_t* n_dev, int D, int H, int W, float* grad_feat,
+                        rslo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSLO_B200_H */

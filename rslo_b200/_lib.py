@@ -1,0 +1,95 @@
+"""ctypes binding of the C ABI in include/rslo_b200.h (rslo_b200/_C/librslo_b200.so).
+
+There is no CPU fallback: if the shared library is missing, importing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "librslo_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"rslo_b200: CUDA library not built ({LIB_PATH} missing). Run `python -c 'import "
+        f"__graft_entry__ as g; g.build()'` or `make -C rslo_b200/csrc`. There is no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/rslo_b200.h one to one
+SIGNATURES = {
+    "rslo_abi_version": (_i, []),
+    "rslo_last_error": (C.c_char_p, []),
+    "rslo_nn_workspace_bytes": (_sz, [_i, _i]),
+    "rslo_nn_exact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "rslo_nn_brute": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "rslo_voxelize_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "rslo_voxelize": (_i, [_vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i, _i, _i, _i, _f, _i,
+                           _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "rslo_vfe_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rslo_site_table_workspace_bytes": (_sz, [_i, _i, _i]),
+    "rslo_site_table_build": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "rslo_subm_table": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rslo_strided_workspace_bytes": (_sz, [_i, _i, _i]),
+    "rslo_strided_table": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rslo_spconv_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "rslo_spconv_transpose_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "rslo_spconv_backward_data": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rslo_spconv_backward_weight": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rslo_dense_from_sites": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rslo_dense_backward": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+}
+
+
+def _bind():
+    missing = []
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if missing:
+        raise ImportError(f"rslo_b200: {LIB_PATH} lacks symbols {missing}; rebuild it")
+
+
+_bind()
+
+
+class RsloError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.rslo_last_error().decode("utf-8", "replace")
+        raise RsloError(f"{what} failed (cudaError {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_WS = {}
+
+
+def workspace(nbytes, slot="default"):
+    """Growable per-(device, slot) scratch buffer; stream-ordered reuse on the current stream."""
+    import torch
+    dev = torch.cuda.current_device()
+    key = (dev, slot)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=f"cuda:{dev}")
+        _WS[key] = buf
+    return buf

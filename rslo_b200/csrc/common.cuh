@@ -1,0 +1,80 @@
+// Shared device utilities for the rslo_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rslo_b200.h"
+
+namespace rslo {
+
+void set_last_error(const char* what, cudaError_t e);
+
+#define RSLO_CHECK_LAUNCH(what)                              \
+    do {                                                     \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) {                            \
+            ::rslo::set_last_error(what, e__);               \
+            return (int)e__;                                 \
+        }                                                    \
+    } while (0)
+
+#define RSLO_CHECK(call)                                     \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) {                            \
+            ::rslo::set_last_error(#call, e__);              \
+            return (int)e__;                                 \
+        }                                                    \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Bump allocator over a caller-provided workspace (256 B aligned slices).
+struct Workspace {
+    char* base;
+    size_t cap, off;
+    __host__ Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {}
+    template <typename T>
+    __host__ T* take(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+        if (off + bytes > cap) return nullptr;
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+static inline size_t ws_round(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+// n = (n_dev ? min(*n_dev, n_cap) : n_cap): every kernel that works on a data-dependent row count
+// takes both, so a whole frame can be enqueued without a host round trip.
+__device__ __forceinline__ int dev_count(const int* n_dev, int n_cap)
+{
+    if (n_dev == nullptr) return n_cap;
+    int n = *n_dev;
+    return n < n_cap ? n : n_cap;
+}
+
+// ---- site table: bitmap over the dense cell grid + exclusive popcount prefix ---------------------
+// cells[w] = {bits, rank of the first set bit of word w}.  lookup(key) -> row index or -1.
+__device__ __forceinline__ int site_lookup(const uint2* __restrict__ cells, const int* __restrict__ perm,
+                                           unsigned key)
+{
+    uint2 w = __ldg(cells + (key >> 5));
+    unsigned bit = 1u << (key & 31);
+    if (!(w.x & bit)) return -1;
+    int r = (int)w.y + __popc(w.x & (bit - 1));
+    return perm ? __ldg(perm + r) : r;
+}
+
+// Exclusive scan of an int array (optionally through a transform) in three launches.
+// SCAN_BLOCK elements per block; block_sums needs cdiv(n, SCAN_BLOCK) + 1 ints.
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+int scan_cells(uint2* cells, int nwords, int* block_sums, int* total_dev, cudaStream_t st);
+int scan_ints(const int* in, int* out, int n, int* block_sums, int* total_dev, cudaStream_t st);
+static inline size_t scan_ws_ints(long long n) { return (size_t)cdiv(n, SCAN_BLOCK) + 8; }
+
+}  // namespace rslo

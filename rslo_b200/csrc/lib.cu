@@ -1,0 +1,15 @@
+// Library-level entry points: ABI version and last-error text.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace rslo {
+static thread_local char g_err[512] = "";
+void set_last_error(const char* what, cudaError_t e)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+}
+}  // namespace rslo
+
+extern "C" int rslo_abi_version(void) { return 1; }
+extern "C" const char* rslo_last_error(void) { return rslo::g_err; }

@@ -1,0 +1,304 @@
+// K4: sparse 3-D convolution over output-stationary neighbour tables (sm_100a), FP32.
+//
+//   out[o,:] = act(scale * (bias + sum_k in[nbr[o,k],:] @ W[k]) + shift)
+//
+// Replaces spconv's per-offset gather -> cuBLAS GEMM -> scatter-add (27 GEMMs + 54 gather/scatter
+// launches per layer) by ONE launch per layer with the bias / BatchNorm-affine / LeakyReLU epilogue
+// fused, no atomics and a fixed summation order (k ascending, then input channel ascending), so the
+// result is deterministic.  One warp owns one output row: the row's K table entries are fetched
+// with one coalesced load, absent offsets are skipped warp-uniformly, each present neighbour row is
+// read with one coalesced 128/256 B load and broadcast through shuffles; W[k] is read through L1
+// (the whole filter bank is <= 442 KB and stays L1/L2 resident).
+// FP32 FFMA on purpose: north_star asks for 1e-4 relative pose/loss parity, which rules out plain
+// TF32/BF16 tensor-core inputs here.
+#include "common.cuh"
+
+namespace rslo {
+namespace {
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+k_spconv_fwd(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap, const int* n_dev, int K,
+             const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ scale,
+             const float* __restrict__ shift, int act, float slope, float* __restrict__ out)
+{
+    constexpr int NA = (CIN + 31) / 32, NO = (COUT + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= dev_count(n_dev, n_cap)) return;
+    float acc[NO];
+#pragma unroll
+    for (int t = 0; t < NO; ++t) acc[t] = 0.f;
+    const int mynb = lane < K ? __ldg(nbr + (size_t)row * K + lane) : -1;
+    unsigned valid = __ballot_sync(0xffffffffu, mynb >= 0);
+    while (valid) {
+        const int k = __ffs(valid) - 1;
+        valid &= valid - 1;
+        const int j = __shfl_sync(0xffffffffu, mynb, k);
+        const float* src = in + (size_t)j * CIN;
+        float a[NA];
+#pragma unroll
+        for (int t = 0; t < NA; ++t) a[t] = (lane + 32 * t < CIN) ? __ldg(src + lane + 32 * t) : 0.f;
+        const float* w = W + (size_t)k * CIN * COUT;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float av = __shfl_sync(0xffffffffu, a[c / 32], c % 32);
+#pragma unroll
+            for (int t = 0; t < NO; ++t)
+                if (COUT % 32 == 0 || lane + 32 * t < COUT)
+                    acc[t] = fmaf(av, __ldg(w + c * COUT + lane + 32 * t), acc[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NO; ++t) {
+        const int co = lane + 32 * t;
+        if (co < COUT) {
+            float v = acc[t];
+            if (bias) v += __ldg(bias + co);
+            if (scale) v = fmaf(v, __ldg(scale + co), __ldg(shift + co));
+            if (act == 1) v = v > 0.f ? v : v * slope;
+            out[(size_t)row * COUT + co] = v;
+        }
+    }
+}
+
+// W [K,Cin,Cout] -> Wt [K,Cout,Cin] with optional offset mirroring (k -> K-1-k).
+__global__ void k_transpose_w(const float* __restrict__ W, int K, int Cin, int Cout, int mirror,
+                              float* __restrict__ Wt)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int tot = K * Cin * Cout;
+    if (t >= tot) return;
+    int ci = t % Cin, co = (t / Cin) % Cout, k = t / (Cin * Cout);
+    int ks = mirror ? K - 1 - k : k;
+    Wt[t] = W[((size_t)ks * Cin + ci) * Cout + co];
+}
+
+// dW[k] += sum over rows o of a chunk with nbr[o,k] >= 0 of in[nbr[o,k],:]^T (x) g[o,:]
+// grid (chunks, K); 256 threads; each thread owns Cin*Cout/256 (>=1) accumulators.
+constexpr int WG_ROWS = 1024;  // rows per chunk
+constexpr int WG_TILE = 32;    // valid rows staged per step
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+k_spconv_wgrad(const float* __restrict__ in, const float* __restrict__ g, const int* __restrict__ nbr,
+               int n_cap, const int* n_dev, int K, float* __restrict__ dW)
+{
+    constexpr int NE = (CIN * COUT + 255) / 256;       // elements per thread
+    __shared__ int s_list_o[WG_ROWS];
+    __shared__ int s_list_j[WG_ROWS];
+    __shared__ int s_count;
+    __shared__ float s_a[WG_TILE][CIN];
+    __shared__ float s_g[WG_TILE][COUT];
+    const int n = dev_count(n_dev, n_cap);
+    const int k = blockIdx.y;
+    const int row0 = blockIdx.x * WG_ROWS;
+    if (row0 >= n) return;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    // compact the chunk's valid (o, j) pairs (order within the chunk is irrelevant to the sum's
+    // value only up to fp32 rounding; we keep row order per warp ballot for reproducibility)
+    for (int base = 0; base < WG_ROWS; base += 256) {
+        int o = row0 + base + threadIdx.x;
+        int j = (o < n) ? __ldg(nbr + (size_t)o * K + k) : -1;
+        unsigned m = __ballot_sync(0xffffffffu, j >= 0);
+        int lane = threadIdx.x & 31;
+        int pos = 0;
+        if (lane == 0 && m) pos = atomicAdd(&s_count, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (j >= 0) {
+            int p = pos + __popc(m & ((1u << lane) - 1));
+            s_list_o[p] = o;
+            s_list_j[p] = j;
+        }
+    }
+    __syncthreads();
+    const int cnt = s_count;
+    float acc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+    for (int base = 0; base < cnt; base += WG_TILE) {
+        const int m = min(WG_TILE, cnt - base);
+        for (int t = threadIdx.x; t < m * CIN; t += 256) {
+            int r = t / CIN, c = t % CIN;
+            s_a[r][c] = __ldg(in + (size_t)s_list_j[base + r] * CIN + c);
+        }
+        for (int t = threadIdx.x; t < m * COUT; t += 256) {
+            int r = t / COUT, c = t % COUT;
+            s_g[r][c] = __ldg(g + (size_t)s_list_o[base + r] * COUT + c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            int idx = threadIdx.x + e * 256;
+            if (idx < CIN * COUT) {
+                int ci = idx / COUT, co = idx % COUT;
+                float s = acc[e];
+                for (int r = 0; r < m; ++r) s = fmaf(s_a[r][ci], s_g[r][co], s);
+                acc[e] = s;
+            }
+        }
+        __syncthreads();
+    }
+    if (cnt == 0) return;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        int idx = threadIdx.x + e * 256;
+        if (idx < CIN * COUT) atomicAdd(dW + (size_t)k * CIN * COUT + idx, acc[e]);
+    }
+}
+
+// column sums: dbias[c] += sum_o g[o,c]
+__global__ void __launch_bounds__(256)
+k_colsum(const float* __restrict__ g, int n_cap, const int* n_dev, int C, float* __restrict__ out)
+{
+    const int n = dev_count(n_dev, n_cap);
+    const int c = threadIdx.x % C;
+    const int rl = threadIdx.x / C, rstep = 256 / C;
+    if (rl >= rstep) return;
+    float s = 0.f;
+    for (int o = blockIdx.x * rstep + rl; o < n; o += gridDim.x * rstep) s += g[(size_t)o * C + c];
+    atomicAdd(out + c, s);
+}
+
+__global__ void k_dense(const float* __restrict__ feat, int C, const uint2* __restrict__ cells,
+                        const int* __restrict__ perm, int ncell, float* __restrict__ dense)
+{
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncell) return;
+    int row = site_lookup(cells, perm, (unsigned)cell);
+    // dense [C, D*H*W]: consecutive threads write consecutive cells of one channel plane
+    if (row < 0) {
+        for (int c = 0; c < C; ++c) dense[(size_t)c * ncell + cell] = 0.f;
+    } else {
+        const float* f = feat + (size_t)row * C;
+        for (int c = 0; c < C; ++c) dense[(size_t)c * ncell + cell] = __ldg(f + c);
+    }
+}
+
+__global__ void k_dense_bwd(const float* __restrict__ gd, int C, const int* __restrict__ coors, int stride,
+                            int n_cap, const int* n_dev, int H, int W, int ncell, float* __restrict__ gf)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int r = (int)(t / C), c = (int)(t % C);
+    if (r >= dev_count(n_dev, n_cap)) return;
+    const int* co = coors + (size_t)r * stride + (stride - 3);
+    int cell = (co[0] * H + co[1]) * W + co[2];
+    gf[t] = gd[(size_t)c * ncell + cell];
+}
+
+#define RSLO_DISPATCH_CC(CIN_, COUT_, ...)                                     \
+    if (Cin == CIN_ && Cout == COUT_) {                                        \
+        constexpr int CI = CIN_, CO = COUT_;                                   \
+        __VA_ARGS__;                                                           \
+        handled = true;                                                        \
+    }
+
+#define RSLO_ALL_SHAPES(...)                                                   \
+    RSLO_DISPATCH_CC(7, 16, __VA_ARGS__)                                       \
+    RSLO_DISPATCH_CC(16, 7, __VA_ARGS__)                                       \
+    RSLO_DISPATCH_CC(16, 16, __VA_ARGS__)                                      \
+    RSLO_DISPATCH_CC(16, 32, __VA_ARGS__)                                      \
+    RSLO_DISPATCH_CC(32, 16, __VA_ARGS__)                                      \
+    RSLO_DISPATCH_CC(32, 32, __VA_ARGS__)                                      \
+    RSLO_DISPATCH_CC(32, 64, __VA_ARGS__)                                      \
+    RSLO_DISPATCH_CC(64, 32, __VA_ARGS__)                                      \
+    RSLO_DISPATCH_CC(64, 64, __VA_ARGS__)
+
+int launch_fwd(const float* in, const int* nbr, int n_cap, const int* n_dev, int K, int Cin, int Cout,
+               const float* W, const float* bias, const float* scale, const float* shift, int act,
+               float slope, float* out, cudaStream_t st)
+{
+    if (n_cap <= 0) return 0;
+    if (K > 32 || K < 1) {
+        set_last_error("spconv: K must be in 1..32", cudaErrorInvalidValue);
+        return (int)cudaErrorInvalidValue;
+    }
+    const int grid = cdiv((long long)n_cap * 32, 256);
+    bool handled = false;
+    RSLO_ALL_SHAPES((k_spconv_fwd<CI, CO><<<grid, 256, 0, st>>>(in, nbr, n_cap, n_dev, K, W, bias, scale,
+                                                               shift, act, slope, out)))
+    if (!handled) {
+        set_last_error("spconv: unsupported (Cin,Cout)", cudaErrorInvalidValue);
+        return (int)cudaErrorInvalidValue;
+    }
+    RSLO_CHECK_LAUNCH("rslo_spconv");
+    return 0;
+}
+
+}  // namespace
+}  // namespace rslo
+
+using namespace rslo;
+
+extern "C" int rslo_spconv_forward(const float* in, const int32_t* nbr, int n_out_cap,
+                                   const int32_t* n_out_dev, int K, int Cin, int Cout, const float* weight,
+                                   const float* bias, const float* scale, const float* shift, int act,
+                                   float slope, float* out, rslo_stream_t stream)
+{
+    return launch_fwd(in, nbr, n_out_cap, n_out_dev, K, Cin, Cout, weight, bias, scale, shift, act, slope,
+                      out, (cudaStream_t)stream);
+}
+
+extern "C" int rslo_spconv_transpose_weight(const float* weight, int K, int Cin, int Cout, int mirror,
+                                            float* weight_t, rslo_stream_t stream)
+{
+    int tot = K * Cin * Cout;
+    k_transpose_w<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, Cin, Cout, mirror, weight_t);
+    RSLO_CHECK_LAUNCH("rslo_spconv_transpose_weight");
+    return 0;
+}
+
+extern "C" int rslo_spconv_backward_data(const float* grad_out, const int32_t* nbr_t, int n_in_cap,
+                                         const int32_t* n_in_dev, int K, int Cin, int Cout,
+                                         const float* weight_t, float* grad_in, rslo_stream_t stream)
+{
+    // the data gradient IS a gather-convolution over the transposed table with W[k]^T
+    return launch_fwd(grad_out, nbr_t, n_in_cap, n_in_dev, K, Cout, Cin, weight_t, nullptr, nullptr, nullptr,
+                      0, 0.f, grad_in, (cudaStream_t)stream);
+}
+
+extern "C" int rslo_spconv_backward_weight(const float* in, const float* grad_out, const int32_t* nbr,
+                                           int n_out_cap, const int32_t* n_out_dev, int K, int Cin,
+                                           int Cout, float* grad_weight, float* grad_bias,
+                                           rslo_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_out_cap <= 0) return 0;
+    dim3 grid(cdiv(n_out_cap, WG_ROWS), K);
+    bool handled = false;
+    RSLO_ALL_SHAPES((k_spconv_wgrad<CI, CO><<<grid, 256, 0, st>>>(in, grad_out, nbr, n_out_cap, n_out_dev, K,
+                                                                 grad_weight)))
+    if (!handled) {
+        set_last_error("spconv wgrad: unsupported (Cin,Cout)", cudaErrorInvalidValue);
+        return (int)cudaErrorInvalidValue;
+    }
+    if (grad_bias) {
+        int blocks = cdiv(n_out_cap, 256 / Cout * 64);
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        k_colsum<<<blocks, 256, 0, st>>>(grad_out, n_out_cap, n_out_dev, Cout, grad_bias);
+    }
+    RSLO_CHECK_LAUNCH("rslo_spconv_backward_weight");
+    return 0;
+}
+
+extern "C" int rslo_dense_from_sites(const float* feat, int C, const uint32_t* cells, const int32_t* perm,
+                                     int D, int H, int W, float* dense, rslo_stream_t stream)
+{
+    int ncell = D * H * W;
+    k_dense<<<cdiv(ncell, 128), 128, 0, (cudaStream_t)stream>>>(feat, C, (const uint2*)cells, perm, ncell, dense);
+    RSLO_CHECK_LAUNCH("rslo_dense_from_sites");
+    return 0;
+}
+
+extern "C" int rslo_dense_backward(const float* grad_dense, int C, const int32_t* coors, int coor_stride,
+                                   int n_cap, const int32_t* n_dev, int D, int H, int W, float* grad_feat,
+                                   rslo_stream_t stream)
+{
+    if (n_cap <= 0) return 0;
+    int ncell = D * H * W;
+    k_dense_bwd<<<cdiv((long long)n_cap * C, 256), 256, 0, (cudaStream_t)stream>>>(
+        grad_dense, C, coors, coor_stride, n_cap, n_dev, H, W, ncell, grad_feat);
+    RSLO_CHECK_LAUNCH("rslo_dense_backward");
+    return 0;
+}

@@ -1,0 +1,248 @@
+"""Torch-tensor wrappers over the C ABI (include/rslo_b200.h).
+
+Every function here launches hand-written sm_100a kernels on the current CUDA stream through
+``rslo_b200._lib``; nothing falls back to PyTorch or the CPU.  ``LAUNCHES`` counts kernel-launching
+ABI calls (bench.py reports it).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream, workspace
+
+LAUNCHES = {"calls": 0}
+
+
+def _count(n=1):
+    LAUNCHES["calls"] += n
+
+
+def _i32(t):
+    assert t.dtype == torch.int32 and t.is_cuda and t.is_contiguous(), "expect contiguous cuda int32"
+    return t
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous(), "expect contiguous cuda float32"
+    return t
+
+
+def _nwords(D, H, W):
+    return (D * H * W + 31) // 32
+
+
+# ------------------------------------------------------------------------------------------------
+# a10: nearest neighbour
+# ------------------------------------------------------------------------------------------------
+def nn_exact(query, target, brute=False):
+    """query [n,3], target [m,3] f32 cuda -> (dist [n] f32, idx [n] i32).  Bit-identical to the
+    reference ChamferDistanceKernel (thirdparty/chamfer_distance/chamfer_distance.cu:6-137)."""
+    q = _f32(query.contiguous())
+    t = _f32(target.contiguous())
+    n, m = q.shape[0], t.shape[0]
+    dist = torch.empty(n, dtype=torch.float32, device=q.device)
+    idx = torch.empty(n, dtype=torch.int32, device=q.device)
+    if n == 0:
+        return dist, idx
+    if brute:
+        check(lib.rslo_nn_brute(ptr(q), n, ptr(t), m, ptr(dist), ptr(idx), stream()), "rslo_nn_brute")
+    else:
+        nb = lib.rslo_nn_workspace_bytes(n, m)
+        ws = workspace(nb, "nn")
+        check(lib.rslo_nn_exact(ptr(q), n, ptr(t), m, ptr(dist), ptr(idx), ptr(ws), ws.numel(), stream()),
+              "rslo_nn_exact")
+    _count()
+    return dist, idx
+
+
+# ------------------------------------------------------------------------------------------------
+# site tables / rulebooks
+# ------------------------------------------------------------------------------------------------
+class SiteTable:
+    """Bitmap + popcount-prefix index of a level's active sites (see csrc/rulebook.cu)."""
+
+    def __init__(self, shape, cells, perm):
+        self.shape = tuple(int(s) for s in shape)    # (D, H, W)
+        self.cells = cells                           # int32 [2*nwords]
+        self.perm = perm                             # int32 [n] or None (rows already sorted)
+
+
+def site_table_build(coors, n, shape, n_dev=None, need_perm=True):
+    D, H, W = (int(s) for s in shape)
+    coors = _i32(coors)
+    cells = torch.empty(2 * _nwords(D, H, W), dtype=torch.int32, device=coors.device)
+    perm = torch.empty(max(n, 1), dtype=torch.int32, device=coors.device) if need_perm else None
+    nb = lib.rslo_site_table_workspace_bytes(D, H, W)
+    ws = workspace(nb, "rulebook")
+    check(lib.rslo_site_table_build(ptr(coors), coors.shape[1], n, ptr(n_dev), D, H, W, ptr(cells), ptr(perm),
+                                    ptr(ws), ws.numel(), stream()), "rslo_site_table_build")
+    _count()
+    return SiteTable((D, H, W), cells, perm)
+
+
+def subm_table(coors, n, table, ksize=(3, 3, 3), n_dev=None):
+    coors = _i32(coors)
+    D, H, W = table.shape
+    K = int(np.prod(ksize))
+    nbr = torch.empty((max(n, 1), K), dtype=torch.int32, device=coors.device)
+    check(lib.rslo_subm_table(ptr(coors), coors.shape[1], n, ptr(n_dev), D, H, W, ptr(table.cells),
+                              ptr(table.perm), ksize[0], ksize[1], ksize[2], ptr(nbr), stream()),
+          "rslo_subm_table")
+    _count()
+    return nbr
+
+
+def out_shape_of(shape, ksize, stride, pad):
+    return tuple((int(s) + 2 * p - k) // st + 1 for s, k, st, p in zip(shape, ksize, stride, pad))
+
+
+def strided_table(coors, n, shape, ksize, stride, pad, n_dev=None, out_cap=None):
+    """-> (out_table, out_coors [cap,4], n_out_dev [1] i32, nbr [cap,K], nbr_inv [n,K])."""
+    coors = _i32(coors)
+    D, H, W = (int(s) for s in shape)
+    oD, oH, oW = out_shape_of(shape, ksize, stride, pad)
+    K = int(np.prod(ksize))
+    if out_cap is None:
+        reach = int(np.prod([-(-k // s) for k, s in zip(ksize, stride)]))
+        out_cap = max(1, min(n * reach, oD * oH * oW))
+    dev = coors.device
+    cells = torch.empty(2 * _nwords(oD, oH, oW), dtype=torch.int32, device=dev)
+    out_coors = torch.empty((out_cap, 4), dtype=torch.int32, device=dev)
+    n_out_dev = torch.empty(1, dtype=torch.int32, device=dev)
+    nbr = torch.empty((out_cap, K), dtype=torch.int32, device=dev)
+    nbr_inv = torch.empty((max(n, 1), K), dtype=torch.int32, device=dev)
+    nb = lib.rslo_strided_workspace_bytes(oD, oH, oW)
+    ws = workspace(nb, "rulebook")
+    check(lib.rslo_strided_table(ptr(coors), coors.shape[1], n, ptr(n_dev), D, H, W, ksize[0], ksize[1],
+                                 ksize[2], stride[0], stride[1], stride[2], pad[0], pad[1], pad[2],
+                                 ptr(cells), ptr(out_coors), out_cap, ptr(n_out_dev), ptr(nbr), ptr(nbr_inv),
+                                 ptr(ws), ws.numel(), stream()), "rslo_strided_table")
+    _count()
+    return SiteTable((oD, oH, oW), cells, None), out_coors, n_out_dev, nbr, nbr_inv
+
+
+# ------------------------------------------------------------------------------------------------
+# voxeliser
+# ------------------------------------------------------------------------------------------------
+def voxelize(points, voxel_size, pc_range, grid_size, max_points=10, max_voxels=40000, block_factor=1,
+             block_size=8, height_threshold=-1.0, batch_idx=0, materialize=True, with_mean=True,
+             with_table=False, coor_stride=4):
+    """points [P,F] f32 cuda -> dict of capacity-sized device tensors + 'n_dev' (device count).
+
+    Replaces `_VoxelGenerator.generate` (rslo/builder/voxel_builder.py:48-54) and, with
+    ``with_mean``, `SimpleVoxel_XYZINormalC.forward` (rslo/models/voxel_encoder.py:272-280)."""
+    pts = _f32(points.contiguous())
+    P, F = pts.shape
+    gx, gy, gz = (int(g) for g in grid_size)
+    dev = pts.device
+    table_d = gz + 1
+    voxels = torch.empty((max_voxels, max_points, F), dtype=torch.float32, device=dev) if materialize else None
+    coors = torch.empty((max_voxels, coor_stride), dtype=torch.int32, device=dev)
+    num = torch.empty(max_voxels, dtype=torch.int32, device=dev)
+    mean = torch.empty((max_voxels, 7), dtype=torch.float32, device=dev) if with_mean else None
+    n_dev = torch.empty(1, dtype=torch.int32, device=dev)
+    cells = perm = None
+    if with_table:
+        cells = torch.empty(2 * _nwords(table_d, gy, gx), dtype=torch.int32, device=dev)
+        perm = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    vs = (C.c_float * 3)(*[float(v) for v in voxel_size])
+    rg = (C.c_float * 6)(*[float(v) for v in pc_range])
+    nb = lib.rslo_voxelize_workspace_bytes(P, gx, gy, table_d, max_voxels)
+    ws = workspace(nb, "voxelize")
+    check(lib.rslo_voxelize(ptr(pts), P, F, vs, rg, gx, gy, gz, max_points, max_voxels, block_factor,
+                            block_size, float(height_threshold), batch_idx, ptr(voxels), ptr(coors),
+                            coor_stride, ptr(num), ptr(mean), ptr(n_dev), ptr(cells), ptr(perm), table_d,
+                            ptr(ws), ws.numel(), stream()), "rslo_voxelize")
+    _count()
+    out = {"voxels": voxels, "coordinates": coors, "num_points_per_voxel": num, "mean": mean, "n_dev": n_dev}
+    if with_table:
+        out["table"] = SiteTable((table_d, gy, gx), cells, perm)
+    return out
+
+
+def vfe_mean(voxels, num_points):
+    v = _f32(voxels.contiguous())
+    npts = _i32(num_points.contiguous())
+    n, mp, F = v.shape
+    mean = torch.empty((n, 7), dtype=torch.float32, device=v.device)
+    check(lib.rslo_vfe_mean(ptr(v), ptr(npts), n, mp, F, ptr(mean), stream()), "rslo_vfe_mean")
+    _count()
+    return mean
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse convolution
+# ------------------------------------------------------------------------------------------------
+def spconv_forward(feat, nbr, n_out, weight, bias=None, scale=None, shift=None, act=0, slope=0.01,
+                   n_out_dev=None):
+    feat = _f32(feat)
+    nbr = _i32(nbr)
+    K = nbr.shape[1]
+    w = _f32(weight.contiguous())
+    Cin, Cout = w.shape[-2], w.shape[-1]
+    assert w.numel() == K * Cin * Cout and feat.shape[1] == Cin
+    out = torch.empty((n_out, Cout), dtype=torch.float32, device=feat.device)
+    if n_out == 0:
+        return out
+    check(lib.rslo_spconv_forward(ptr(feat), ptr(nbr), n_out, ptr(n_out_dev), K, Cin, Cout, ptr(w),
+                                  ptr(bias), ptr(scale), ptr(shift), act, float(slope), ptr(out), stream()),
+          "rslo_spconv_forward")
+    _count()
+    return out
+
+
+def spconv_backward_data(grad_out, nbr_t, n_in, weight, mirror):
+    g = _f32(grad_out.contiguous())
+    nbr_t = _i32(nbr_t)
+    K = nbr_t.shape[1]
+    w = _f32(weight.contiguous())
+    Cin, Cout = w.shape[-2], w.shape[-1]
+    wt = torch.empty(K * Cin * Cout, dtype=torch.float32, device=g.device)
+    check(lib.rslo_spconv_transpose_weight(ptr(w), K, Cin, Cout, 1 if mirror else 0, ptr(wt), stream()),
+          "rslo_spconv_transpose_weight")
+    grad_in = torch.empty((n_in, Cin), dtype=torch.float32, device=g.device)
+    if n_in > 0:
+        check(lib.rslo_spconv_backward_data(ptr(g), ptr(nbr_t), n_in, None, K, Cin, Cout, ptr(wt),
+                                            ptr(grad_in), stream()), "rslo_spconv_backward_data")
+    _count(2)
+    return grad_in
+
+
+def spconv_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=True):
+    feat = _f32(feat)
+    g = _f32(grad_out.contiguous())
+    nbr = _i32(nbr)
+    K = nbr.shape[1]
+    Cin, Cout = weight_shape[-2], weight_shape[-1]
+    gw = torch.zeros(tuple(weight_shape), dtype=torch.float32, device=g.device)
+    gb = torch.zeros(Cout, dtype=torch.float32, device=g.device) if need_bias else None
+    if n_out > 0:
+        check(lib.rslo_spconv_backward_weight(ptr(feat), ptr(g), ptr(nbr), n_out, None, K, Cin, Cout,
+                                              ptr(gw), ptr(gb), stream()), "rslo_spconv_backward_weight")
+    _count(2)
+    return gw, gb
+
+
+def dense_from_sites(feat, table):
+    feat = _f32(feat)
+    D, H, W = table.shape
+    Cc = feat.shape[1]
+    dense = torch.empty((Cc * D, H, W), dtype=torch.float32, device=feat.device)
+    check(lib.rslo_dense_from_sites(ptr(feat), Cc, ptr(table.cells), ptr(table.perm), D, H, W, ptr(dense),
+                                    stream()), "rslo_dense_from_sites")
+    _count()
+    return dense
+
+
+def dense_backward(grad_dense, coors, n, shape, C_):
+    g = _f32(grad_dense.contiguous())
+    coors = _i32(coors)
+    D, H, W = shape
+    gf = torch.empty((n, C_), dtype=torch.float32, device=g.device)
+    if n > 0:
+        check(lib.rslo_dense_backward(ptr(g), C_, ptr(coors), coors.shape[1], n, None, D, H, W, ptr(gf),
+                                      stream()), "rslo_dense_backward")
+    _count()
+    return gf

@@ -1,0 +1,225 @@
+"""Parity of the CUDA kernels (through the C ABI) against the CPU oracle.  Integer / index outputs
+are compared bit-exactly; floating-point outputs with the tolerance written at each check."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import native as onat
+from oracle import sparse as osp
+from rslo_b200.data import synthetic
+
+pytestmark = pytest.mark.gpu
+
+VS = [0.1, 0.1, 0.2]
+RG = [-70.4, -38.4, -3, 70.4, 38.4, 5]
+GRID = [1408, 768, 40]
+
+
+@pytest.fixture(scope="module")
+def K(cuda):
+    from rslo_b200 import kernels
+    return kernels
+
+
+@pytest.fixture(scope="module")
+def scan_pair():
+    return synthetic.make_pair(0)
+
+
+def _vox_gpu(K, pts, **kw):
+    out = K.voxelize(torch.from_numpy(pts).cuda(), VS, RG, GRID, **kw)
+    n = int(out["n_dev"].item())
+    return out, n
+
+
+@pytest.mark.parametrize("max_voxels,thr", [(40000, -1.0), (20000, -1.0), (40000, 0.2), (3000, 0.5)])
+def test_voxelize_bit_exact(K, scan_pair, max_voxels, thr):
+    pts = scan_pair[0]
+    ref = onat.voxelize(pts, VS, RG, 10, max_voxels, 1, 8, thr)
+    out, n = _vox_gpu(K, pts, max_voxels=max_voxels, height_threshold=thr)
+    assert n == ref["voxels"].shape[0]
+    assert np.array_equal(out["coordinates"][:n, 1:].cpu().numpy(), ref["coordinates"])
+    assert (out["coordinates"][:n, 0] == 0).all()
+    assert np.array_equal(out["num_points_per_voxel"][:n].cpu().numpy(), ref["num_points_per_voxel"])
+    assert np.array_equal(out["voxels"][:n].cpu().numpy(), ref["voxels"])     # bit-exact copies
+    mean_ref = osp.vfe_mean(ref["voxels"], ref["num_points_per_voxel"]).numpy()
+    # fp32 sum-order tolerance
+    np.testing.assert_allclose(out["mean"][:n].cpu().numpy(), mean_ref, rtol=1e-5, atol=1e-6)
+    m2 = K.vfe_mean(out["voxels"][:n], out["num_points_per_voxel"][:n]).cpu().numpy()
+    np.testing.assert_allclose(m2, mean_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_voxelize_edge_cases(K):
+    # all points outside the range -> zero voxels; one voxel with more points than max_points;
+    # shuffled (non scan-ordered) ragged input
+    far = np.full((100, 7), 1000.0, np.float32)
+    out, n = _vox_gpu(K, far)
+    assert n == 0
+    one = np.zeros((37, 7), np.float32)
+    one[:, :3] = [1.01, 2.02, 0.03]
+    one[:, 3] = np.arange(37)
+    ref = onat.voxelize(one, VS, RG)
+    out, n = _vox_gpu(K, one)
+    assert n == 1 and int(out["num_points_per_voxel"][0]) == 10
+    assert np.array_equal(out["voxels"][:1].cpu().numpy(), ref["voxels"])
+    rng = np.random.default_rng(3)
+    shuf = synthetic.make_pair(1)[0]
+    shuf = shuf[rng.permutation(len(shuf))][:50001]
+    ref = onat.voxelize(shuf, VS, RG)
+    out, n = _vox_gpu(K, shuf)
+    assert n == len(ref["coordinates"])
+    assert np.array_equal(out["coordinates"][:n, 1:].cpu().numpy(), ref["coordinates"])
+    assert np.array_equal(out["voxels"][:n].cpu().numpy(), ref["voxels"])
+
+
+def _tables_gpu(K, coors4, n, shape):
+    t = {}
+    tab0 = K.site_table_build(coors4, n, shape)
+    t["subm0"] = K.subm_table(coors4, n, tab0)
+    tab1, c1, n1d, t["conv3d2"], t["conv3d2_inv"] = K.strided_table(coors4, n, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    n1 = int(n1d.item())
+    t["L1"] = (c1, n1, tab1)
+    t["subm1"] = K.subm_table(c1, n1, tab1)
+    tab2, c2, n2d, t["conv3d3"], t["conv3d3_inv"] = K.strided_table(c1, n1, tab1.shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    n2 = int(n2d.item())
+    t["L2"] = (c2, n2, tab2)
+    t["subm2"] = K.subm_table(c2, n2, tab2)
+    tab3, c3, n3d, t["conv3d4"], _ = K.strided_table(c2, n2, tab2.shape, (3, 3, 3), (2, 2, 2), (0, 1, 1))
+    n3 = int(n3d.item())
+    t["L3"] = (c3, n3, tab3)
+    t["subm3"] = K.subm_table(c3, n3, tab3)
+    tab4, c4, n4d, t["conv3d5"], _ = K.strided_table(c3, n3, tab3.shape, (3, 1, 1), (2, 1, 1), (0, 0, 0))
+    n4 = int(n4d.item())
+    t["L4"] = (c4, n4, tab4)
+    return t
+
+
+def test_rulebook_bit_exact(K, scan_pair):
+    pts = scan_pair[1]
+    vox = onat.voxelize(pts, VS, RG)
+    co = vox["coordinates"]
+    n = len(co)
+    shape = [41, 768, 1408]
+    ref = osp.build_tables(co, shape)
+    coors4 = torch.from_numpy(np.concatenate([np.zeros((n, 1), np.int32), co], 1)).cuda()
+    t = _tables_gpu(K, coors4, n, shape)
+    for lvl in ["L1", "L2", "L3", "L4"]:
+        c, nn_, tab = t[lvl]
+        assert nn_ == len(ref[lvl].coors), lvl
+        assert list(tab.shape) == list(ref[lvl].shape), lvl
+        assert np.array_equal(c[:nn_, 1:].cpu().numpy(), ref[lvl].coors), lvl
+    sizes = {"subm0": n, "conv3d2": t["L1"][1], "conv3d2_inv": n, "subm1": t["L1"][1], "conv3d3": t["L2"][1],
+             "conv3d3_inv": t["L1"][1], "subm2": t["L2"][1], "conv3d4": t["L3"][1], "subm3": t["L3"][1],
+             "conv3d5": t["L4"][1]}
+    for key, rows in sizes.items():
+        assert np.array_equal(t[key][:rows].cpu().numpy(), ref[key]), key
+
+
+@pytest.mark.parametrize("cin,cout,K_", [(7, 16, 27), (16, 16, 27), (16, 32, 27), (32, 32, 27), (32, 64, 27),
+                                         (64, 64, 27), (64, 64, 3), (64, 32, 27), (32, 16, 27), (16, 7, 27)])
+def test_spconv_forward_and_wgrad(K, cin, cout, K_):
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    n_in, n_out = 3000, 2500
+    nbr = torch.randint(0, n_in, (n_out, K_), generator=g, dtype=torch.int32)
+    nbr[torch.rand((n_out, K_), generator=g) < 0.7] = -1
+    feat = torch.randn((n_in, cin), generator=g)
+    w = torch.randn((K_, cin, cout), generator=g) * 0.1
+    b = torch.randn(cout, generator=g)
+    ref = torch.nn.functional.leaky_relu(osp.gather_conv(feat, nbr, w, b), 0.01)
+    out = K.spconv_forward(feat.cuda(), nbr.cuda(), n_out, w.cuda(), b.cuda(), act=1, slope=0.01)
+    # fp32 with a different summation order
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+    featr = feat.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    o = osp.gather_conv(featr, nbr, wr, br)
+    go = torch.randn(o.shape, generator=g)
+    o.backward(go)
+    gw, gb = K.spconv_backward_weight(feat.cuda(), go.cuda(), nbr.cuda(), n_out, (K_, cin, cout))
+    np.testing.assert_allclose(gw.cpu().numpy(), wr.grad.numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(gb.cpu().numpy(), br.grad.numpy(), rtol=1e-3, atol=1e-3)
+
+
+def test_spconv_backward_data_on_real_tables(K, scan_pair):
+    pts = scan_pair[0][:60000]
+    vox = onat.voxelize(pts, VS, RG)
+    co = vox["coordinates"]
+    n = len(co)
+    shape = [41, 768, 1408]
+    nbr = onat.subm_table(co, shape)
+    c1, s1, nb_s, nb_inv = onat.strided_table(co, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    g = torch.Generator().manual_seed(5)
+    # (forward table, transposed table, n_in, mirror): submanifold, strided, inverse
+    for (table, table_t, n_in, mirror) in [(nbr, nbr, n, True), (nb_s, nb_inv, n, False),
+                                           (nb_inv, nb_s, len(c1), False)]:
+        feat = torch.randn((n_in, 16), generator=g, requires_grad=True)
+        w = (torch.randn((27, 16, 32), generator=g) * 0.1).requires_grad_(True)
+        o = osp.gather_conv(feat, table, w)
+        go = torch.randn(o.shape, generator=g)
+        o.backward(go)
+        gi = K.spconv_backward_data(go.cuda(), torch.from_numpy(table_t).cuda(), n_in, w.detach().cuda(), mirror)
+        np.testing.assert_allclose(gi.cpu().numpy(), feat.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_dense(K):
+    rng = np.random.default_rng(0)
+    D, H, W = 2, 96, 176
+    cells = rng.choice(D * H * W, 9000, replace=False)
+    cells.sort()
+    co = np.stack([np.zeros_like(cells), cells // (H * W), (cells // W) % H, cells % W], 1).astype(np.int32)
+    coors = torch.from_numpy(co).cuda()
+    tab = K.site_table_build(coors, len(co), (D, H, W), need_perm=False)
+    feat = torch.randn(len(co), 64)
+    dense = K.dense_from_sites(feat.cuda(), tab).cpu()
+    ref = torch.zeros(64, D, H, W)
+    ref[:, co[:, 1], co[:, 2], co[:, 3]] = feat.t()
+    assert torch.equal(dense, ref.view(64 * D, H, W))
+    gd = torch.randn(64 * D, H, W)
+    gf = K.dense_backward(gd.cuda(), coors, len(co), (D, H, W), 64).cpu()
+    assert torch.equal(gf, gd.view(64, D, H, W)[:, co[:, 1], co[:, 2], co[:, 3]].t())
+
+
+def _ref_cuda_nn(q, t):
+    """The reference's own CUDA kernel, when oracle/_ref was built (it travels with the repo)."""
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "cd_ref.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("cd_ref", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    d = torch.zeros(1, q.shape[0], device="cuda")
+    i = torch.zeros(1, q.shape[0], dtype=torch.int32, device="cuda")
+    mod.forward_cuda_one_direction(q[None].contiguous(), t[None].contiguous(), d, i)
+    torch.cuda.synchronize()
+    return d[0], i[0]
+
+
+@pytest.mark.parametrize("n,m,kind", [(5000, 5003, "uniform"), (3000, 1500, "uniform"), (40000, 40000, "lidar"),
+                                      (20000, 777, "lidar"), (4096, 4096, "ties")])
+def test_nn_bit_exact(K, scan_pair, n, m, kind):
+    rng = np.random.default_rng(n + m)
+    if kind == "uniform":
+        q = rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+        t = rng.uniform(-50, 50, (m, 3)).astype(np.float32)
+    elif kind == "ties":
+        # integer lattice: many exactly equal distances -> the lowest index must win
+        q = rng.integers(-8, 8, (n, 3)).astype(np.float32)
+        t = rng.integers(-8, 8, (m, 3)).astype(np.float32)
+    else:
+        a = onat.voxelize(scan_pair[0], VS, RG)
+        b = onat.voxelize(scan_pair[1], VS, RG)
+        q = osp.vfe_mean(a["voxels"], a["num_points_per_voxel"]).numpy()[:n, :3].copy()
+        t = osp.vfe_mean(b["voxels"], b["num_points_per_voxel"]).numpy()[:m, :3].copy()
+    d_ref, i_ref = onat.nn(q, t, fused=True)
+    qc, tc = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    for brute in (False, True):
+        d, i = K.nn_exact(qc, tc, brute=brute)
+        assert np.array_equal(i.cpu().numpy(), i_ref), f"idx mismatch brute={brute}"
+        assert np.array_equal(d.cpu().numpy(), d_ref), f"dist mismatch brute={brute}"
+    r = _ref_cuda_nn(qc, tc)
+    if r is not None:   # pin oracle AND kernel against the reference's own CUDA kernel
+        assert np.array_equal(r[1].cpu().numpy(), i_ref)
+        assert np.array_equal(r[0].cpu().numpy(), d_ref)
