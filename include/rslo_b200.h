@@ -85,7 +85,8 @@ int rslo_subm_table(const int32_t* coors, int coor_stride, int n_cap, const int3
                     int32_t* nbr, rslo_stream_t stream);
 /* Strided conv: output site set (sorted by cell index), its site table, and both tables.
  * out_coors [out_cap,4] (b,z,y,x); nbr [out_cap,K]; nbr_inv [n_cap,K] (the SparseInverseConv3d
- * table: nbr_inv[i*K+k] = o iff nbr[o*K+k] = i); n_out_dev device int. */
+ * table: nbr_inv[i*K+k] = o iff nbr[o*K+k] = i); n_out_dev: device int[2] = {min(count, out_cap),
+ * count} — count > out_cap means the caller must retry with a larger out_cap. */
 size_t rslo_strided_workspace_bytes(int oD, int oH, int oW);
 int rslo_strided_table(const int32_t* coors, int coor_stride, int n_cap, const int32_t* n_dev,
                        int D, int H, int W, int kd, int kh, int kw, int sd, int sh, int sw, int pd,
@@ -127,6 +128,20 @@ int rslo_dense_from_sites(const float* feat, int C, const uint32_t* cells, const
 int rslo_dense_backward(const float* grad_dense, int C, const int32_t* coors, int coor_stride,
                         int n_cap, const int32_t* n_dev, int D, int H, int W, float* grad_feat,
                         rslo_stream_t stream);
+
+/* ---- a12: weighted Kabsch alignment (no host round trip) -----------------------------------------
+ * Replaces SVDHead.forward (rslo/layers/svd.py:13-64) as driven by the ICP refinement in
+ * rslo/core/losses.py:440-488.  src/tgt [n,3] f32 row-major; weight [n] or NULL (ones); mask [n]
+ * 0/1 floats or NULL; optional ROI test dist[i] < *dist_threshold (both device, may be NULL).
+ * Means are unweighted over the selected points, H = sum m w (x-xbar)(y-ybar)^T, R = V U^T with the
+ * det<0 reflection fix; writes the reference's return values R_out = R^T [9], t_out = -R^T t [3].
+ * comp_R [9] / comp_t [3] (may be NULL) are updated in place as comp_R <- R_out comp_R,
+ * comp_t <- R_out comp_t + t_out (losses.py:463-465). */
+size_t rslo_kabsch_workspace_bytes(void);
+int rslo_kabsch(const float* src, const float* tgt, const float* weight, const float* mask,
+                const float* dist, const float* dist_threshold, int n, float* R_out, float* t_out,
+                float* comp_R, float* comp_t, void* workspace, size_t workspace_bytes,
+                rslo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -4,3 +4,21 @@ Host code mirrors the reference's `rslo.models` / `rslo.layers` / builder surfac
 hand-written sm_100a CUDA kernels behind the C ABI in include/rslo_b200.h (rslo_b200/_C).
 """
 __version__ = "0.1.0"
+
+import os as _os
+
+DEFAULT_CONFIG = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "config", "kitti_ours.prototxt")
+
+
+def build_network(config_path=None, testing=False, measure_time=False, seed=None):
+    """prototxt -> (net, voxel_generator), the two builder calls `train_hdf5.py:92-101` makes."""
+    import torch
+
+    from .builder import config as _config
+    from .builder import second_builder, voxel_builder
+    cfg = _config.load(config_path or DEFAULT_CONFIG)
+    vg = voxel_builder.build(cfg.model.second.voxel_generator)
+    if seed is not None:
+        torch.manual_seed(seed)
+    net = second_builder.build(cfg.model.second, vg, measure_time=measure_time, testing=testing)
+    return net, vg

@@ -39,6 +39,8 @@ SIGNATURES = {
     "rslo_spconv_backward_data": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rslo_spconv_backward_weight": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rslo_dense_from_sites": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rslo_kabsch_workspace_bytes": (_sz, []),
+    "rslo_kabsch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rslo_dense_backward": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
 }
 

@@ -1,0 +1,58 @@
+"""Voxel generator builder (`rslo/builder/voxel_builder.py:36-95`)."""
+import numpy as np
+import torch
+
+from .. import kernels as K
+
+
+class _VoxelGenerator:
+    """Same surface as the reference wrapper over spconv.utils.VoxelGenerator: `.voxel_size`,
+    `.point_cloud_range`, `.grid_size`, `.generate(points, max_voxels) -> dict`.  `generate` runs the
+    CUDA voxeliser (csrc/voxelize.cu) on the current device and returns numpy arrays like the
+    reference; `generate_device` returns device tensors (+ fused VFE means) without the copies."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000, full_mean=False,
+                 block_filtering=True, block_factor=1, block_size=8, height_threshold=0.2):
+        assert not full_mean
+        self.voxel_size = np.array(voxel_size, dtype=np.float32)
+        self.point_cloud_range = np.array(point_cloud_range, dtype=np.float32)
+        self.max_num_points = int(max_num_points)
+        self.max_voxels = int(max_voxels)
+        self.max_voxels_per_call = 40000      # preprocess.max_number_of_voxels of the shipped configs
+        self.block_filtering = block_filtering
+        self.block_factor, self.block_size = int(block_factor), int(block_size)
+        self.height_threshold = float(height_threshold)
+
+    @property
+    def grid_size(self):
+        g = (self.point_cloud_range[3:] - self.point_cloud_range[:3]) / self.voxel_size
+        return np.round(g).astype(np.int64)
+
+    def generate_device(self, points, max_voxels=None, materialize=True, with_mean=False, with_table=False):
+        if not torch.is_tensor(points):
+            points = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32))
+        points = points.cuda(non_blocking=True)
+        return K.voxelize(points, self.voxel_size, self.point_cloud_range, self.grid_size,
+                          max_points=self.max_num_points, max_voxels=int(max_voxels or self.max_voxels),
+                          block_factor=self.block_factor, block_size=self.block_size,
+                          height_threshold=self.height_threshold, materialize=materialize, with_mean=with_mean,
+                          with_table=with_table, coor_stride=3 if not with_table else 4)
+
+    def generate(self, points, max_voxels=None):
+        out = self.generate_device(points, max_voxels)
+        n = int(out["n_dev"].item())
+        return {"voxels": out["voxels"][:n].cpu().numpy(), "coordinates": out["coordinates"][:n].cpu().numpy(),
+                "num_points_per_voxel": out["num_points_per_voxel"][:n].cpu().numpy()}
+
+
+def build(voxel_config):
+    """`voxel_builder.py:57-95`: forces block filtering on and fills its defaults."""
+    voxel_config.block_filtering = True
+    voxel_config.block_factor = max(1, voxel_config.block_factor)
+    voxel_config.block_size = voxel_config.block_size if voxel_config.block_size > 0 else 8
+    voxel_config.height_threshold = voxel_config.height_threshold if voxel_config.height_threshold != 0 else 0.2
+    return _VoxelGenerator(
+        voxel_size=list(voxel_config.voxel_size), point_cloud_range=list(voxel_config.point_cloud_range),
+        max_num_points=voxel_config.max_number_of_points_per_voxel, max_voxels=20000, full_mean=False,
+        block_filtering=voxel_config.block_filtering, block_factor=voxel_config.block_factor,
+        block_size=voxel_config.block_size, height_threshold=voxel_config.height_threshold)

@@ -1,0 +1,174 @@
+"""Loss stack of the hot path (`rslo/core/losses.py:56-113,144-197,301-507`).
+
+The consistency loss is restated without host round trips: where the reference compacts the ROI
+points with boolean-mask indexing (a `nonzero` sync per use, `losses.py:416-420,441-447`), branches
+on `det < 0` and wraps `torch.inverse` in try/except, this version keeps all N points and applies
+the ROI as a 0/1 factor inside the reductions — the same sums over the same points — and uses
+closed-form 3x3 inverse / determinant.  Nearest neighbours come from csrc/nn.cu, the ICP alignment
+from csrc/kabsch.cu.
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import kernels as K
+from ..layers.svd import SVDHead
+from ..thirdparty.chamfer_distance.chamfer_distance import OneDirectionChamferDistanceWithIdx
+from ..utils import pose_utils
+
+
+class Loss(nn.Module):
+    """`losses.py:56-113`."""
+
+    def __init__(self, loss_weight=1):
+        super().__init__()
+        self._loss_weight = loss_weight
+
+    def forward(self, prediction_tensor, target_tensor, ignore_nan_targets=False, scope=None, **params):
+        if ignore_nan_targets:
+            target_tensor = torch.where(torch.isnan(target_tensor), prediction_tensor, target_tensor)
+        ret = self._compute_loss(prediction_tensor, target_tensor, **params)
+        if isinstance(ret, (list, tuple)):
+            return [self._loss_weight * ret[0]] + list(ret[1:])
+        return self._loss_weight * ret     # the reference evaluates _compute_loss a second time here
+
+
+class AdaptiveWeightedL2Loss(Loss):
+    """`losses.py:144-197`: L_b = sum(mask (p-t)^2) / (sum(mask)+1e-12); loss = sum_b w_b e^-a L_b + a."""
+
+    def __init__(self, init_alpha, learn_alpha=True, loss_weight=1, focal_gamma=0, balance_scale=1):
+        super().__init__(loss_weight)
+        self.learn_alpha = learn_alpha
+        self.alpha = nn.Parameter(torch.Tensor([init_alpha]), requires_grad=learn_alpha)
+        self.focal_gamma = focal_gamma
+
+    def _compute_loss(self, prediction_tensor, target_tensor, mask=None, alpha=None, focal_gamma=None):
+        if focal_gamma is None:
+            focal_gamma = self.focal_gamma
+        _alpha = self.alpha
+        mask = torch.ones_like(target_tensor) if mask is None else mask.expand_as(target_tensor)
+        diff = prediction_tensor - target_tensor
+        square_diff = (diff * diff) * mask
+        dims = list(range(1, prediction_tensor.dim()))
+        loss = torch.sum(square_diff, dim=dims) / (torch.sum(mask, dim=dims) + 1e-12)
+        focal_weight = (torch.exp(-_alpha) * loss) ** focal_gamma
+        focal_weight = focal_weight / (torch.sum(focal_weight) + 1e-12)
+        loss = focal_weight * (torch.exp(-_alpha) * loss)
+        return loss.sum() + _alpha
+
+
+def span_cov2(cov_param_pred):
+    """7 raw parameters -> 3x3 covariance V diag(l1, l1+l2, l1+l2+l3) V^T (`losses.py:348-363`)."""
+    p = cov_param_pred
+    l1 = p[:, 0:1]
+    l2 = l1 + p[:, 1:2]
+    l3 = l2 + p[:, 2:3]
+    q = p[:, 3:] / (torch.norm(p[:, 3:], dim=-1, keepdim=True) + 1e-9)
+    eigvec = pose_utils.quaternion_to_rotation_matrix(q)          # (x,y,z,w), as the reference feeds it
+    lam = torch.cat([l1, l2, l3], dim=1)
+    return (eigvec * lam[:, None, :]) @ eigvec.transpose(-1, -2)
+
+
+def inv_det_3x3(m):
+    """Closed-form inverse and determinant of a batch of 3x3 matrices."""
+    a, b, c = m[:, 0, 0], m[:, 0, 1], m[:, 0, 2]
+    d, e, f = m[:, 1, 0], m[:, 1, 1], m[:, 1, 2]
+    g, h, i = m[:, 2, 0], m[:, 2, 1], m[:, 2, 2]
+    A = e * i - f * h
+    B = -(d * i - f * g)
+    Cc = d * h - e * g
+    det = a * A + b * B + c * Cc
+    adj = torch.stack([A, -(b * i - c * h), b * f - c * e,
+                       B, a * i - c * g, -(a * f - c * d),
+                       Cc, -(a * h - b * g), a * e - b * d], dim=-1).view(-1, 3, 3)
+    return adj / det[:, None, None], det
+
+
+class Aleat5_1ChamferL2NormalWeightedALLSVDLoss(Loss):
+    """`losses.py:301-507`: NN association, Mahalanobis residual under the summed predicted
+    covariances + log-det regulariser, then `icp_iter` rounds of normal-weighted Kabsch refinement
+    that return the residual pose (res_R, res_T) used as pseudo label."""
+
+    def __init__(self, init_alpha=0, learn_alpha=False, loss_weight=1, focal_gamma=0, n_samples=-1,
+                 penalize_ratio=0.95, sample_block_size=(0.1, 1, 1), norm=True, pred_downsample_ratio=1,
+                 reg_weight=0.001, sph_weight=1):
+        super().__init__(loss_weight=loss_weight)
+        self.learn_alpha = learn_alpha
+        self.alpha = nn.Parameter(torch.Tensor([init_alpha]), requires_grad=learn_alpha)
+        self.focal_gamma = focal_gamma
+        self.n_samples = n_samples
+        self.penalize_ratio = penalize_ratio
+        self.sample_block_size = sample_block_size
+        self.cd = OneDirectionChamferDistanceWithIdx()
+        self.norm = norm
+        self.svd = SVDHead()
+        assert pred_downsample_ratio >= 1, "pred_downsample_ratio < 1 is not used by the shipped configs"
+        self.pred_downsample_ratio = pred_downsample_ratio
+        self.reg_weight = reg_weight
+        self.sph_weight = sph_weight
+
+    def _roi_threshold(self, dist):
+        """kth value at the penalize_ratio quantile, floored at 1.0 (`losses.py:326-334`)."""
+        flat = dist.reshape(-1)
+        m, _ = torch.kthvalue(flat, 1 + int(flat.numel() * self.penalize_ratio), dim=-1)
+        return torch.max(m, torch.ones_like(m))
+
+    def _compute_loss(self, xyz_pred, xyz_target, cov_pred, cov_target, R_pred, t_pred, normal_pred,
+                      normal_target, mask=None, alpha=None, focal_gamma=None, icp_iter=1):
+        assert mask is None, "the hot path passes mask=None (voxel_odom_net.py:704)"
+        if focal_gamma is None:
+            focal_gamma = self.focal_gamma
+        _alpha = self.alpha
+        B = xyz_pred.shape[0]
+        loss = 0
+        res_R, res_T = [], []
+        eye = torch.eye(3, device=xyz_pred.device, dtype=xyz_pred.dtype)
+        for b in range(B):
+            src = xyz_pred[b].detach().contiguous()
+            tgt_full = xyz_target[b].detach().contiguous()
+            dist, idx = K.nn_exact(src, tgt_full)
+            idxl = idx.long()
+            xyz_assoc = xyz_target[b][idxl]
+            thr = self._roi_threshold(dist)
+            roi = dist < thr
+            cnt = roi.sum().to(xyz_pred.dtype)
+
+            cov_p = span_cov2(cov_pred[b])
+            cov_t = span_cov2(cov_target[b])[idxl]
+            Rb = R_pred[b].detach()
+            sigma = cov_p + Rb @ cov_t @ Rb.transpose(-1, -2)
+            # rows outside the ROI do not enter the loss: neutralise them BEFORE the nonlinear ops so
+            # neither their values nor their gradients can produce inf/nan
+            sigma = torch.where(roi[:, None, None], sigma, eye)
+            diff_vec = torch.where(roi[:, None], xyz_pred[b] - xyz_assoc, torch.zeros_like(xyz_assoc))
+            sigma_inv, det = inv_det_3x3(sigma)
+            square_diff = (diff_vec[:, None, :] @ sigma_inv @ diff_vec[:, :, None]).view(-1)
+            logdet = torch.where(roi, 0.5 * torch.log(det), torch.zeros_like(det))
+            loss_ = square_diff.sum() / cnt + self.reg_weight * (logdet.sum() / cnt)
+            loss = loss + loss_
+
+            # ICP refinement on detached points (losses.py:440-488)
+            with torch.no_grad():
+                nrm = normal_pred[b].detach()
+                wgt = F.cosine_similarity(nrm, xyz_assoc.detach() - src, dim=-1).abs()
+                res_r_ = eye.clone()
+                res_t_ = torch.zeros(3, device=src.device, dtype=src.dtype)
+                cur_tgt, cur_dist, cur_thr = xyz_assoc.detach().contiguous(), dist, thr
+                for icp_i in range(icp_iter):
+                    K.kabsch(src, cur_tgt, weight=(wgt * wgt).contiguous(), dist=cur_dist,
+                             dist_threshold=cur_thr, comp_R=res_r_, comp_t=res_t_)
+                    if icp_i < icp_iter - 1:
+                        moved = tgt_full @ res_r_.t() + res_t_
+                        cur_dist, i2 = K.nn_exact(src, moved)
+                        cur_tgt = moved[i2.long()]
+                        wgt = F.cosine_similarity(nrm, cur_tgt - src, dim=-1).abs()
+                        cur_thr = self._roi_threshold(cur_dist)
+            res_R.append(res_r_[None])
+            res_T.append(res_t_[None])
+        res_R = torch.cat(res_R, dim=0)
+        res_T = torch.cat(res_T, dim=0)
+        loss = loss / B
+        focal_weight = (torch.exp(-_alpha) * loss) ** focal_gamma
+        focal_weight = focal_weight / (torch.sum(focal_weight) + 1e-12)
+        loss = focal_weight * (torch.exp(-_alpha) * loss)
+        return loss.sum() + _alpha, res_R, res_T

@@ -124,9 +124,10 @@ __global__ void k_strided_table(const int* __restrict__ coors, int stride, int n
     nbr_inv[t] = o;
 }
 
+// n[1] = raw number of output sites, n[0] = min(raw, cap): callers detect overflow from n[1] > cap
 __global__ void k_clamp_count(int* n, int cap)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0 && *n > cap) *n = cap;
+    if (threadIdx.x == 0 && blockIdx.x == 0) n[0] = n[1] > cap ? cap : n[1];
 }
 
 }  // namespace
@@ -201,12 +202,12 @@ extern "C" int rslo_strided_table(const int32_t* coors, int coor_stride, int n_c
     }
     RSLO_CHECK(cudaMemsetAsync(out_cells, 0, nwords * sizeof(uint2), st));
     if (n_cap <= 0) {
-        RSLO_CHECK(cudaMemsetAsync(n_out_dev, 0, sizeof(int), st));
+        RSLO_CHECK(cudaMemsetAsync(n_out_dev, 0, 2 * sizeof(int), st));
         return 0;
     }
     const int G = cdiv((long long)n_cap * K, 256);
     k_strided_mark<<<G, 256, 0, st>>>(coors, coor_stride, n_cap, n_dev, g, out_cells);
-    int rc = scan_cells(out_cells, (int)nwords, block_sums, n_out_dev, st);
+    int rc = scan_cells(out_cells, (int)nwords, block_sums, n_out_dev + 1, st);
     if (rc) return rc;
     k_clamp_count<<<1, 32, 0, st>>>(n_out_dev, out_cap);
     k_strided_coords<<<cdiv(nwords, 256), 256, 0, st>>>(out_cells, (int)nwords, g, out_cap, out_coors);

@@ -99,7 +99,7 @@ def out_shape_of(shape, ksize, stride, pad):
 
 
 def strided_table(coors, n, shape, ksize, stride, pad, n_dev=None, out_cap=None):
-    """-> (out_table, out_coors [cap,4], n_out_dev [1] i32, nbr [cap,K], nbr_inv [n,K])."""
+    """-> (out_table, out_coors [cap,4], n_out_dev [2] i32 {clamped, raw}, nbr [cap,K], nbr_inv [n,K])."""
     coors = _i32(coors)
     D, H, W = (int(s) for s in shape)
     oD, oH, oW = out_shape_of(shape, ksize, stride, pad)
@@ -110,7 +110,7 @@ def strided_table(coors, n, shape, ksize, stride, pad, n_dev=None, out_cap=None)
     dev = coors.device
     cells = torch.empty(2 * _nwords(oD, oH, oW), dtype=torch.int32, device=dev)
     out_coors = torch.empty((out_cap, 4), dtype=torch.int32, device=dev)
-    n_out_dev = torch.empty(1, dtype=torch.int32, device=dev)
+    n_out_dev = torch.empty(2, dtype=torch.int32, device=dev)
     nbr = torch.empty((out_cap, K), dtype=torch.int32, device=dev)
     nbr_inv = torch.empty((max(n, 1), K), dtype=torch.int32, device=dev)
     nb = lib.rslo_strided_workspace_bytes(oD, oH, oW)
@@ -246,3 +246,21 @@ def dense_backward(grad_dense, coors, n, shape, C_):
                                       stream()), "rslo_dense_backward")
     _count()
     return gf
+
+
+# ------------------------------------------------------------------------------------------------
+# a12: weighted Kabsch
+# ------------------------------------------------------------------------------------------------
+def kabsch(src, tgt, weight=None, mask=None, dist=None, dist_threshold=None, comp_R=None, comp_t=None):
+    """src/tgt [n,3] -> (R [3,3], t [3]) with SVDHead's return convention (rslo/layers/svd.py:57-64).
+    Sync-free: selection by `mask` and/or `dist < dist_threshold` happens inside the reduction."""
+    src = _f32(src.contiguous())
+    tgt = _f32(tgt.contiguous())
+    n = src.shape[0]
+    R = torch.empty((3, 3), dtype=torch.float32, device=src.device)
+    t = torch.empty(3, dtype=torch.float32, device=src.device)
+    ws = workspace(lib.rslo_kabsch_workspace_bytes(), "kabsch")
+    check(lib.rslo_kabsch(ptr(src), ptr(tgt), ptr(weight), ptr(mask), ptr(dist), ptr(dist_threshold), n, ptr(R),
+                          ptr(t), ptr(comp_R), ptr(comp_t), ptr(ws), ws.numel(), stream()), "rslo_kabsch")
+    _count()
+    return R, t

@@ -1,0 +1,271 @@
+"""Odometry head (`rslo/models/odom_pred.py:44-435`, `odom_pred_base.py:25-346`,
+`custom_resnet_spc.py:224-298`): masked ResNet encoder-decoder over the concatenated BEV maps of a
+frame pair -> dense per-cell (t,q) map + softmax confidences -> confidence-voted global (t,q).
+
+Module tree and parameter names follow the reference so its checkpoints load unchanged (485 state_dict
+entries, tests/golden/state_dict_shapes.json).  Differences that do not change any output:
+  * MaskConv mask propagation through the encoder is skipped (the propagated masks are never read);
+  * the T=1 and T=20 confidences share one pass of the confidence conv stack (the reference runs the
+    stack twice on the same values, `odom_pred.py:242-258`);
+  * cell-anchor grids are cached instead of rebuilt per call.
+The 2-D convolutions are dense contractions and run through cuDNN in FP32.
+"""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from ..data.dataset import cell_anchors, from_pointwise_local_transformation_tch
+from ..layers.common import ParameterLayer
+from ..layers.confidence import ConfidenceModule
+from ..layers.MaskConv import MaskConv
+from ..layers.SparseConv import SPC_BN2d, SPC_ReLU, SPC_SyncBN2d
+from ..torchplus import Empty, change_default_args
+from ..utils.pose_utils import rotate_vec_by_q
+
+REGISTERED_ODOM_PRED_CLASSES = {}
+
+
+def register_odom_pred(cls, name=None):
+    name = cls.__name__ if name is None else name
+    assert name not in REGISTERED_ODOM_PRED_CLASSES, f"exist class: {REGISTERED_ODOM_PRED_CLASSES}"
+    REGISTERED_ODOM_PRED_CLASSES[name] = cls
+    return cls
+
+
+def get_odom_class(name):
+    assert name in REGISTERED_ODOM_PRED_CLASSES, f"available class: {REGISTERED_ODOM_PRED_CLASSES}"
+    return REGISTERED_ODOM_PRED_CLASSES[name]
+
+
+def SPC_add(a, b):
+    if isinstance(a, (list, tuple)):
+        m = None if a[1] is None or b[1] is None else ((a[1] + b[1]) / 2).float()
+        return [a[0] + b[0], m]
+    return a + b
+
+
+class BasicBlock(nn.Module):
+    """`custom_resnet_spc.py:224-298` with use_se = use_sa = False."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, BN=None, Conv2d=None, groups=1):
+        super().__init__()
+        self.conv1 = Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=False, groups=groups)
+        self.bn1 = BN(planes)
+        self.relu = SPC_ReLU(inplace=True)
+        self.conv2 = Conv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False, groups=groups)
+        self.bn2 = BN(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        residual = x
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        if self.downsample is not None:
+            residual = self.downsample(x)
+        return self.relu(SPC_add(out, residual))
+
+
+def _conf_stack(cin, BN, ReLU):
+    return nn.Sequential(nn.Conv2d(cin, 64, kernel_size=3, padding=1), BN(64), ReLU(),
+                         nn.Conv2d(64, 32, kernel_size=3, padding=1), BN(32), ReLU(),
+                         nn.Conv2d(32, 1, kernel_size=1))
+
+
+@register_odom_pred
+class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
+    def __init__(self, point_cloud_range=None, enc_use_norm=True, seq_len=1, layer_nums=(3, 5, 5),
+                 layer_strides=(2, 2, 2), num_filters=(128, 128, 256), upsample_strides=(1, 2, 4),
+                 num_upsample_filters=(256, 256, 256), num_input_features=128, encode_background_as_zeros=True,
+                 use_groupnorm=False, bn_type="BN", num_groups=32, dropout=0.2, pooling_type="avg_pool",
+                 pooling_size=1, cycle_constraint=False, conv_type="official", odom_format="rx+t",
+                 pred_pyramid_motion=False, use_deep_supervision=False, use_loss_mask=True,
+                 use_dynamic_mask=False, dense_predict=False, use_correlation=False, conf_type="linear",
+                 use_SPGN=False, sync_bn=False, use_leakyReLU=False, dropout_input=False, first_conv_groups=1,
+                 use_se=False, use_sa=False, use_svd=False, cubic_pred_height=0, name="odomPred", **kwargs):
+        super().__init__()
+        assert conv_type == "mask_conv", "only conv_type 'mask_conv' is built (shipped configs)"
+        assert odom_format in ["rx+t", "r(x+t)"]
+        assert bn_type in ["BN", "SyncBN"], "only (Sync)BN heads are built (shipped configs)"
+        assert conf_type in ["linear", "softmax"]
+        assert not (use_groupnorm or use_dynamic_mask or use_correlation or use_SPGN or use_leakyReLU or
+                    dropout_input or use_se or use_sa or use_svd), "option outside the shipped configs"
+        assert dropout > 0
+        layer_nums, layer_strides = list(layer_nums), list(layer_strides)
+        num_filters, upsample_strides = list(num_filters), list(upsample_strides)
+        num_upsample_filters = list(num_upsample_filters)
+        self.name = name
+        self.conf_type = conf_type
+        self._cubic_pred_height = cubic_pred_height
+        self.point_cloud_range = point_cloud_range
+        self.odom_format = odom_format
+        self._use_mask_conv = True
+        self._use_sparse_conv = False
+        self.dense_predict = dense_predict
+        self.use_svd = use_svd
+        self._cycle_constraint = cycle_constraint
+        self._num_input_features = num_input_features
+        self._enc_use_norm = enc_use_norm
+        self.pred_pyramid_motion = use_deep_supervision          # (sic) odom_pred_base.py:112
+
+        bn_cls = SPC_SyncBN2d if (bn_type == "SyncBN" or sync_bn) else SPC_BN2d
+        self.BatchNorm2d = change_default_args(eps=1e-3, momentum=0.01)(bn_cls)
+        self.ReLU = SPC_ReLU
+        Conv2d = change_default_args(bias=True)(nn.Conv2d)
+        BN, ReLU = self.BatchNorm2d, self.ReLU
+
+        in_filters = [num_input_features, *num_filters[:-1]]
+        blocks, skip_blocks, deblocks = [], [], []
+        for i, layer_num in enumerate(layer_nums):
+            block, nout = self._make_layer(in_filters[i], num_filters[i], layer_num, stride=layer_strides[i],
+                                           first_groups=first_conv_groups if i == 0 else 1, use_norm=enc_use_norm)
+            blocks.append(block)
+            skip_blocks.append(nn.Sequential(Conv2d(nout, nout, kernel_size=3, stride=1, padding=1), BN(nout), ReLU()))
+        py_blocks = []
+        for i in range(len(num_upsample_filters)):
+            cin = num_filters[-1] * 2 if i == 0 else num_upsample_filters[i - 1] + num_filters[-(i + 1)]
+            deblocks.append(nn.Sequential(nn.Upsample(scale_factor=upsample_strides[i]),
+                                          nn.Conv2d(cin, num_upsample_filters[i], kernel_size=3, stride=1, padding=1),
+                                          BN(num_upsample_filters[i]), ReLU()))
+            if self.pred_pyramid_motion:
+                c = num_upsample_filters[i]
+                py_blocks.append(nn.Sequential(nn.Conv2d(c, c // 2, kernel_size=3, stride=1, padding=1), BN(c // 2), ReLU(),
+                                               nn.Conv2d(c // 2, 64, kernel_size=3, stride=1, padding=1), BN(64), ReLU(),
+                                               nn.Conv2d(64, 7, 1, stride=1)))
+        if self.pred_pyramid_motion:
+            self.mask_gen_pools = nn.ModuleList([nn.MaxPool2d(kernel_size=3, stride=s, padding=1) for s in upsample_strides])
+        self.blocks = nn.ModuleList(blocks)
+        self.deblocks = nn.ModuleList(deblocks)
+        self.skip_blocks = nn.ModuleList(skip_blocks)
+        self.pyramid_motion_blocks = nn.ModuleList(py_blocks)
+        c_last = num_upsample_filters[-1]
+        self.tq_map_conv = nn.Sequential(nn.Conv2d(c_last, 64, kernel_size=3, padding=1), BN(64), ReLU(),
+                                         nn.Conv2d(64, 32, kernel_size=3, padding=1), BN(32), ReLU(),
+                                         nn.Conv2d(32, 7, kernel_size=1))
+        self.q_map_conf = ConfidenceModule(_conf_stack(c_last, BN, ReLU), conf_type=conf_type)
+        self.t_map_conf = ConfidenceModule(_conf_stack(c_last, BN, ReLU), conf_type=conf_type)
+        self.pool = nn.AdaptiveAvgPool2d((pooling_size, pooling_size)) if pooling_type == "avg_pool" \
+            else nn.AdaptiveMaxPool2d((pooling_size, pooling_size))
+        self.fc1 = nn.Linear(num_filters[-1] * pooling_size * pooling_size * seq_len, 1024)
+        self.odom_dropout = nn.Dropout(p=dropout)
+        self.dense_dropout = nn.Dropout2d(p=dropout)
+        self.fc2 = nn.Linear(1024, 7)
+        self.softmax = nn.Softmax(dim=-1)
+        self.SPGN = Empty()
+        self.dynamic_sigma = ParameterLayer(torch.ones(1) * 0.1, requires_grad=True)
+        self.pyramid_tconf_blocks = nn.ModuleList(
+            [ConfidenceModule(_conf_stack(c, BN, ReLU), conf_type=conf_type) for c in num_upsample_filters]
+            if self.pred_pyramid_motion else [])
+        self.pyramid_qconf_blocks = nn.ModuleList(
+            [ConfidenceModule(_conf_stack(c, BN, ReLU), conf_type=conf_type) for c in num_upsample_filters]
+            if self.pred_pyramid_motion else [])
+        self.hier_weight_gen = nn.AvgPool2d(3, 2, padding=1)
+
+        # init (`odom_pred.py:381-389`)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d) and m.weight.requires_grad:
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def _make_layer(self, inplanes, planes, num_blocks, stride=1, first_groups=1, use_norm=True):
+        conv2d = change_default_args(propagate_mask=False)(MaskConv)
+        BN = self.BatchNorm2d if use_norm else Empty
+        downsample = None
+        if stride != 1 or inplanes != planes:
+            downsample = nn.Sequential(conv2d(inplanes, planes, kernel_size=1, stride=stride, bias=False,
+                                              groups=first_groups), BN(planes))
+        layers = [BasicBlock(inplanes, planes, stride, downsample, BN=BN, Conv2d=conv2d, groups=first_groups)]
+        for _ in range(1, num_blocks):
+            layers.append(BasicBlock(planes, planes, BN=BN, Conv2d=conv2d))
+        return nn.Sequential(*layers), planes
+
+    @staticmethod
+    def create_cycle_constraint_data(xs):
+        """all ordered pairs i<j of the sequence (`odom_pred_base.py:305-324`)."""
+        assert len(xs) >= 2
+        b, C, H, W = xs[0].shape
+        x1, x2 = [], []
+        for i in range(len(xs)):
+            for j in range(i + 1, len(xs)):
+                x1.append(xs[i])
+                x2.append(xs[j])
+        return [torch.stack(x1, dim=1).reshape(-1, C, H, W), torch.stack(x2, dim=1).reshape(-1, C, H, W)]
+
+    def forward(self, xs, tq_map_gt=None, local_spatial_features=None, **kwargs):
+        if not isinstance(xs, list):
+            xs = [xs]
+        if self._cycle_constraint:
+            xs = self.create_cycle_constraint_data(xs)
+        input_mask_bool = (torch.sum(xs[0], dim=1, keepdim=True) != 0).detach_()
+        input_mask = input_mask_bool.to(dtype=xs[0].dtype)
+        x = torch.cat(xs, dim=1)
+        ups = []
+        for i in range(len(self.blocks)):
+            x = self.blocks[i](x)
+            ups.append(self.skip_blocks[i](x[0]))
+        x = x[0]
+        x_middle = x
+        py_masks = []
+        if self.pred_pyramid_motion:
+            p_mask = input_mask
+            for i in range(len(self.deblocks) - 1):
+                p_mask = self.mask_gen_pools[-(i + 1)](p_mask)
+                py_masks.append(p_mask)
+            py_masks.reverse()
+        py_preds = []
+        for i in range(len(self.deblocks)):
+            x = torch.cat([x, ups[-(i + 1)]], dim=1)
+            x = self.deblocks[i](x)
+            if self.pred_pyramid_motion and i < len(self.deblocks) - 1:
+                py_pred = self.pyramid_motion_blocks[i](x)
+                py_preds.append([py_pred * (py_masks[i] > 0).to(dtype=py_pred.dtype), py_masks[i]])
+        x_tail = x
+        tq_map = self.tq_map_conv(x)
+        q_map = tq_map[:, 3:] / torch.norm(tq_map[:, 3:], dim=1, keepdim=True)
+        tq_map = torch.cat([tq_map[:, :3], q_map], dim=1)
+
+        odoms = []
+        tq_map_g = tq_map
+        t_conf = torch.ones_like(tq_map[:, :1])
+        r_conf = torch.ones_like(tq_map[:, :1])
+        if self.dense_predict:
+            t_conf, t_logit = self.t_map_conf(x_tail, extra_mask=input_mask, return_logit=True)
+            r_conf, r_logit = self.q_map_conf(x_tail, extra_mask=input_mask, return_logit=True)
+            tq_map_g = from_pointwise_local_transformation_tch(tq_map, self.point_cloud_range)
+            odoms += self.aggregate_tq([tq_map_g], t_confs=[t_conf], r_confs=[r_conf])
+            temp_t_conf = self.t_map_conf(None, extra_mask=input_mask, temperature=20, logit=t_logit.detach())
+            temp_r_conf = self.q_map_conf(None, extra_mask=input_mask, temperature=20, logit=r_logit.detach())
+            temp_tq_conf = torch.cat([temp_t_conf, temp_r_conf], dim=1).detach()
+            pyramid_motion = py_preds + [[tq_map * input_mask, input_mask * temp_tq_conf]]
+            for p in range(2, len(pyramid_motion) + 1):
+                pyramid_motion[-p][1] = pyramid_motion[-p][1] * self.hier_weight_gen(pyramid_motion[-(p - 1)][1])
+        else:
+            pyramid_motion = []
+            x = self.pool(x_middle)
+            x = self.fc1(x.view(x.size(0), -1))
+            x = self.fc2(self.odom_dropout(F.relu(x)))
+            odoms += [x]
+
+        translations, rotations = [], []
+        for x in odoms:
+            translation, rotation = x[:, :3], x[:, 3:]
+            if self.odom_format == "r(x+t)":
+                translation = rotate_vec_by_q(translation, rotation)
+            rotation = rotation / (torch.norm(rotation, dim=1, keepdim=True) + 1e-12)
+            translations.append(translation)
+            rotations.append(rotation)
+        return {"translation_preds": translations, "rotation_preds": rotations, "tq_map_g": tq_map_g * input_mask,
+                "pyramid_motion": pyramid_motion, "transformed_inputs": None, "t_conf": t_conf, "r_conf": r_conf}
+
+    def aggregate_tq(self, tq_maps_g, t_confs, r_confs):
+        """confidence-weighted vote (`odom_pred.py:347-357`, use_svd False)."""
+        odoms = []
+        for tq_map_g, t_conf, r_conf in zip(tq_maps_g, t_confs, r_confs):
+            t = torch.sum(tq_map_g[:, :3] * t_conf, dim=(2, 3)) / (torch.sum(t_conf, dim=(2, 3)) + 1e-12)
+            q = torch.sum(tq_map_g[:, 3:] * r_conf, dim=(2, 3)) / (torch.sum(r_conf, dim=(2, 3)) + 1e-12)
+            odoms.append(torch.cat([t, q], dim=-1))
+        return odoms

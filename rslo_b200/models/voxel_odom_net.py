@@ -1,0 +1,406 @@
+"""Network orchestrator `UnVoxelOdomNetICP3` (`rslo/models/voxel_odom_net.py:46-834`).
+
+`net(example) -> dict` keeps the reference's contract.  Two input forms:
+  * the reference's: ``example["voxels"|"num_points"|"coordinates"][t]`` produced by a voxel
+    generator (CPU worker or `rslo_b200.builder.voxel_builder`), ``example["num_voxels"][t]``;
+  * B200-native: ``example["points"][t]`` = raw scan ``[P,7]`` on the device; the fused
+    scatter-voxeliser + VFE kernel (csrc/voxelize.cu) runs inside forward and also hands its site
+    table to the sparse encoder, so the 11 MB/frame `voxels` tensor is never materialised.
+"""
+import time
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import kernels as K
+from ..data.dataset import generate_pointwise_local_transformation_tch
+from ..torchplus import roll
+from ..utils import pose_utils
+from . import middle, odom_pred, voxel_encoder
+
+REGISTERED_NETWORK_CLASSES = {}
+
+
+def register_voxelnet(cls, name=None):
+    name = cls.__name__ if name is None else name
+    assert name not in REGISTERED_NETWORK_CLASSES, f"exist class: {REGISTERED_NETWORK_CLASSES}"
+    REGISTERED_NETWORK_CLASSES[name] = cls
+    return cls
+
+
+def get_voxelnet_class(name):
+    assert name in REGISTERED_NETWORK_CLASSES, f"available class: {REGISTERED_NETWORK_CLASSES}"
+    return REGISTERED_NETWORK_CLASSES[name]
+
+
+def create_cycle_constraint_data(xs, cat_dim=1):
+    """all ordered pairs i<j (`voxel_odom_net.py:800-818`)."""
+    assert len(xs) >= 2
+    shape = xs[0].shape
+    x1, x2 = [], []
+    for i in range(len(xs)):
+        for j in range(i + 1, len(xs)):
+            x1.append(xs[i])
+            x2.append(xs[j])
+    return [torch.stack(x1, dim=cat_dim).reshape(-1, *shape[1:]), torch.stack(x2, dim=cat_dim).reshape(-1, *shape[1:])]
+
+
+def _detach_tree(x, to_cpu=False):
+    if isinstance(x, torch.Tensor):
+        x = x.detach()
+        return x.cpu() if to_cpu else x
+    if isinstance(x, (list, tuple)):
+        return [_detach_tree(v, to_cpu) for v in x]
+    if isinstance(x, dict):
+        return {k: _detach_tree(v, to_cpu) for k, v in x.items()}
+    return x
+
+
+@register_voxelnet
+class UnVoxelOdomNetICP3(nn.Module):
+    def __init__(self, output_shape, pc_range=None, num_input_features=4, vfe_class_name="VoxelFeatureExtractor",
+                 vfe_num_filters=(32, 128), with_distance=False, middle_class_name="SparseMiddleExtractor",
+                 middle_num_input_features=-1, middle_num_filters_d1=(64,), middle_num_filters_d2=(64, 64),
+                 middle_use_leakyReLU=False, middle_bn_type="BN", middle_relu_type="ReLU",
+                 odom_class_name="ResNetOdomPred", odom_num_input_features=-1, odom_layer_nums=(3, 5, 5),
+                 odom_layer_strides=(2, 2, 2), odom_num_filters=(128, 128, 256), odom_upsample_strides=(1, 2, 4),
+                 odom_num_upsample_filters=(256, 256, 256), odom_pooling_type="avg_pool", odom_pooling_size=1,
+                 odom_cycle_constraint=False, odom_conv_type="official", odom_format="rx+t",
+                 odom_pred_pyramid_motion=False, odom_use_deep_supervision=False, odom_dense_predict=False,
+                 odom_use_loss_mask=True, odom_use_dynamic_mask=False, odom_use_corr=False, odom_dropout=0.2,
+                 odom_bn_type="BN", odom_conf_type="linear", odom_use_SPGN=False, odom_use_leakyReLU=False,
+                 odom_first_conv_groups=1, odom_use_se=False, odom_use_sa=False, vfe_use_norm=True,
+                 odom_enc_use_norm=True, odom_use_svd=False, odom_dropout_input=False, odom_cubic_pred_height=5,
+                 freeze_bn=False, freeze_bn_affine=False, freeze_bn_start_step=1e20, sync_bn=False, use_GN=False,
+                 encode_background_as_zeros=True, rotation_loss=None, translation_loss=None,
+                 pyramid_rotation_loss=None, pyramid_translation_loss=None, consistency_loss=None,
+                 measure_time=False, voxel_generator=None, pyloss_exp_w_base=0.5, testing=False, icp_iter=2,
+                 name="voxel_odom_net", **kwargs):
+        super().__init__()
+        self.name = name
+        self.testing = testing
+        self._encode_background_as_zeros = encode_background_as_zeros
+        self._num_input_features = num_input_features
+        self.voxel_generator = voxel_generator
+        self._rotation_loss = rotation_loss
+        self._translation_loss = translation_loss
+        self._pyramid_rotation_loss = pyramid_rotation_loss
+        self._pyramid_translation_loss = pyramid_translation_loss
+        self._consistency_loss = consistency_loss
+        assert pyloss_exp_w_base > 0
+        self._pyloss_exp_w_base = pyloss_exp_w_base
+        assert icp_iter > 0, "The parameter of icp_iter should be larger than 0."
+        self.icp_iter = icp_iter
+        self.measure_time = measure_time
+        self.voxel_feature_extractor = voxel_encoder.get_vfe_class(vfe_class_name)(
+            num_input_features, vfe_use_norm, num_filters=vfe_num_filters, with_distance=with_distance,
+            voxel_size=self.voxel_generator.voxel_size, pc_range=self.voxel_generator.point_cloud_range)
+        self.middle_feature_extractor = middle.get_middle_class(middle_class_name)(
+            output_shape, bn_type=middle_bn_type, use_GN=use_GN, sync_bn=sync_bn, use_leakyReLU=middle_use_leakyReLU,
+            relu_type=middle_relu_type, num_input_features=middle_num_input_features,
+            num_filters_down1=middle_num_filters_d1, num_filters_down2=middle_num_filters_d2)
+        self.middle_feature_extractor_name = middle_class_name
+        self.odom_predictor = odom_pred.get_odom_class(odom_class_name)(
+            bn_type=odom_bn_type, enc_use_norm=odom_enc_use_norm, conv_type=odom_conv_type,
+            layer_nums=odom_layer_nums, layer_strides=odom_layer_strides, num_filters=odom_num_filters,
+            upsample_strides=odom_upsample_strides, num_upsample_filters=odom_num_upsample_filters,
+            num_input_features=odom_num_input_features * 2, pooling_type=odom_pooling_type,
+            pooling_size=odom_pooling_size, encode_background_as_zeros=True, use_groupnorm=use_GN, num_groups=32,
+            dropout=odom_dropout, cycle_constraint=odom_cycle_constraint,
+            pred_pyramid_motion=odom_pred_pyramid_motion, use_deep_supervision=odom_use_deep_supervision,
+            use_loss_mask=odom_use_loss_mask, use_dynamic_mask=odom_use_dynamic_mask, odom_format=odom_format,
+            point_cloud_range=pc_range, dense_predict=odom_dense_predict, use_correlation=odom_use_corr,
+            conf_type=odom_conf_type, use_SPGN=odom_use_SPGN, use_leakyReLU=odom_use_leakyReLU,
+            dropout_input=odom_dropout_input, first_conv_groups=odom_first_conv_groups, use_se=odom_use_se,
+            use_sa=odom_use_sa, use_svd=odom_use_svd, cubic_pred_height=odom_cubic_pred_height,
+            freeze_bn=freeze_bn, freeze_bn_affine=freeze_bn_affine, sync_bn=sync_bn, name="odomPred")
+        self.freeze_bn = freeze_bn
+        self.freeze_bn_affine = freeze_bn_affine
+        self.freeze_bn_start_step = freeze_bn_start_step
+        self.register_buffer("global_step", torch.LongTensor(1).zero_())
+        self._step_host = None          # host mirror of global_step: no device read per query
+        self.warm_flag = False
+        self._time_dict, self._time_total_dict, self._time_count_dict = {}, {}, {}
+
+    # ---- bookkeeping (voxel_odom_net.py:206-287) -------------------------------------------------
+    def train(self, mode=True):
+        super().train(mode)
+        if self.freeze_bn and self.get_global_step() >= self.freeze_bn_start_step:
+            for m in self.modules():
+                if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                    m.eval()
+                    if self.freeze_bn_affine:
+                        if m.weight is not None:
+                            m.weight.requires_grad = False
+                        if m.bias is not None:
+                            m.bias.requires_grad = False
+        return self
+
+    def start_timer(self, *names):
+        if not self.measure_time:
+            return
+        torch.cuda.synchronize()
+        for name in names:
+            self._time_dict[name] = time.time()
+
+    def end_timer(self, name):
+        if not self.measure_time or name not in self._time_dict:
+            return
+        torch.cuda.synchronize()
+        dt = time.time() - self._time_dict[name]
+        self._time_count_dict[name] = self._time_count_dict.get(name, 0) + 1
+        self._time_total_dict[name] = self._time_total_dict.get(name, 0.0) + dt
+        self._time_dict[name] = 0
+
+    def clear_timer(self):
+        self._time_count_dict.clear()
+        self._time_dict.clear()
+        self._time_total_dict.clear()
+
+    def get_avg_time_dict(self):
+        return {name: val / max(1, self._time_count_dict[name]) for name, val in self._time_total_dict.items()}
+
+    def update_global_step(self):
+        self.global_step += 1
+        if self._step_host is not None:
+            self._step_host += 1
+
+    def get_global_step(self):
+        if self._step_host is None:
+            self._step_host = int(self.global_step.cpu().numpy()[0])
+        return self._step_host
+
+    def clear_global_step(self):
+        self.global_step.zero_()
+        self._step_host = 0
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._step_host = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def clear_metrics(self):
+        pass
+
+    # ---- tq target maps (voxel_odom_net.py:293-322) ----------------------------------------------
+    def gen_tq_maps(self, odometries, spatial_size, pc_range, cubic_tq_map=False):
+        if len(spatial_size) == 2:
+            spatial_size = [1] + list(spatial_size)
+        grid_size = np.array(list(spatial_size[::-1]))
+        voxel_size = (pc_range[3:] - pc_range[0:3]) / grid_size
+        spatial_size = grid_size if cubic_tq_map else grid_size[:2]
+        origin_loc = ((0 - pc_range[0]) / (pc_range[3] - pc_range[0]) * grid_size[0],
+                      (pc_range[4] - 0) / (pc_range[4] - pc_range[1]) * grid_size[1],
+                      (0 - pc_range[2]) / (pc_range[5] - pc_range[2]) * grid_size[2])
+        tq_maps = [generate_pointwise_local_transformation_tch(tq, spatial_size=spatial_size, origin_loc=origin_loc,
+                                                               voxel_size=voxel_size, inv_trans_factor=-1)
+                   for tq in odometries]
+        return [torch.stack(tq_maps, dim=0)]
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def _voxelize_on_device(self, points):
+        vg = self.voxel_generator
+        out = K.voxelize(points, vg.voxel_size, vg.point_cloud_range, vg.grid_size, max_points=vg.max_num_points,
+                         max_voxels=vg.max_voxels_per_call, block_factor=vg.block_factor, block_size=vg.block_size,
+                         height_threshold=vg.height_threshold, materialize=False, with_mean=True, with_table=True)
+        n = int(out["n_dev"].item())
+        return out["mean"][:n], out["coordinates"][:n], out["num_points_per_voxel"][:n], out["table"]
+
+    def network_forward(self, voxels, num_points, coors, batch_size, example):
+        assert len(voxels) == len(num_points) == len(coors), "The lengths should be same."
+        tables = example.get("_site_tables", [None] * len(voxels))
+        self.start_timer("voxel_feature_extractor")
+        voxel_features = [self.voxel_feature_extractor(voxels[i], num_points[i], coors[i]) for i in range(len(voxels))]
+        self.end_timer("voxel_feature_extractor")
+        self.start_timer("middle forward")
+        spatial_features, middle_conf_preds = [], []
+        for i in range(len(voxel_features)):
+            ret, conf_pred = self.middle_feature_extractor(voxel_features[i], coors[i], batch_size, table0=tables[i])
+            spatial_features.append(ret)
+            middle_conf_preds.append(conf_pred)
+        self.end_timer("middle forward")
+        preds_dict = self.odom_predictor(spatial_features, tq_map_gt=None)
+        if self.training or self.testing:
+            with torch.no_grad():
+                preds_dict["feature_mask"] = (torch.sum(torch.cat(spatial_features, dim=1), dim=1, keepdim=True) != 0).float()
+                disp = [torch.mean(s.detach(), dim=1, keepdim=True) for s in spatial_features]
+                preds_dict["middle_feature"] = [(d - torch.min(d)) / (torch.max(d) - torch.min(d) + 1e-12) for d in disp]
+        preds_dict["middle_conf_preds"] = middle_conf_preds
+        preds_dict["voxel_features"] = voxel_features
+        preds_dict["voxel_coords"] = coors
+        preds_dict["normal_preds"] = []
+        return preds_dict
+
+    def forward(self, example):
+        if "points" in example:
+            voxels, num_points, coors, tables = [], [], [], []
+            for pts in example["points"]:
+                m, c, npts, tab = self._voxelize_on_device(pts)
+                voxels.append(m)
+                coors.append(c)
+                num_points.append(npts)
+                tables.append(tab)
+            example = dict(example)
+            example["_site_tables"] = tables
+            batch_size_dev = 1
+        else:
+            voxels, num_points, coors = example["voxels"], example["num_points"], example["coordinates"]
+            if len(num_points[0].shape) == 2:       # padded multi-gpu layout (voxel_odom_net.py:480-507)
+                vb, nb, cb = [], [], []
+                for t in range(len(voxels)):
+                    nv = example["num_voxels"][t].cpu().numpy().reshape(-1)
+                    vb.append(torch.cat([voxels[t][i, :k] for i, k in enumerate(nv)], dim=0))
+                    nb.append(torch.cat([num_points[t][i, :k] for i, k in enumerate(nv)], dim=0))
+                    cb.append(torch.cat([coors[t][i, :k] for i, k in enumerate(nv)], dim=0))
+                voxels, num_points, coors = vb, nb, cb
+            batch_size_dev = example["num_voxels"][0].shape[0]
+        preds_dict = self.network_forward(voxels, num_points, coors, batch_size_dev, example=example)
+        if self.training:
+            ret = self.loss(example, preds_dict)
+            ret2 = {
+                "middle_feature": preds_dict["middle_feature"], "feature_mask": preds_dict["feature_mask"],
+                "t_conf": preds_dict["t_conf"], "r_conf": preds_dict["r_conf"],
+                "pyramid_motion": preds_dict["pyramid_motion"], "dynamic_sigma": -1, "transformed_inputs": None,
+                "tq_map_g": preds_dict["tq_map_g"], "local_motion": None, "down_masks": None,
+                "middle_conf_preds": list(preds_dict["middle_conf_preds"]),
+            }
+            # the reference copies these ~10 maps to the host every step (voxel_odom_net.py:535-538);
+            # `host_outputs=False` in the example keeps them on the device (detached)
+            ret.update(_detach_tree(ret2, to_cpu=example.get("host_outputs", True)))
+            return ret
+        t_pred, r_pred = preds_dict["translation_preds"], preds_dict["rotation_preds"]
+        if isinstance(t_pred, (list, tuple)):
+            t_pred = t_pred[-1]
+        if isinstance(r_pred, (list, tuple)):
+            r_pred = r_pred[-1]
+        out = {"translation_preds": t_pred.detach(), "rotation_preds": r_pred.detach()}
+        if self.testing:
+            out["middle_conf_preds"] = _detach_tree(list(preds_dict["middle_conf_preds"]))
+            out["voxel_features"] = _detach_tree(preds_dict["voxel_features"])
+            out["normal_preds"] = []
+            out["tq_map_g"] = preds_dict["tq_map_g"].detach()
+            out["pyramid_motion"] = _detach_tree(preds_dict["pyramid_motion"])
+            out["t_conf"] = preds_dict["t_conf"].detach()
+            out["r_conf"] = preds_dict["r_conf"].detach()
+            out["normal_gt"] = example.get("normal_gt", None)
+        return out
+
+    # ---- loss (voxel_odom_net.py:324-376, 586-798) -------------------------------------------------
+    def loss(self, example, preds_dict):
+        T_preds, R_preds = preds_dict["translation_preds"], preds_dict["rotation_preds"]
+        dtype = T_preds[0].dtype
+        self.start_timer("Create_loss forward")
+        pyramid_loss = torch.zeros([1], dtype=dtype, device=T_preds[0].device)
+        translation_loss, rotation_loss, pyramid_T_losses, pyramid_R_losses, C_loss = self.create_loss(
+            preds_dict, example, self._translation_loss, self._rotation_loss,
+            pyramid_rotation_loss=self._pyramid_rotation_loss,
+            pyramid_translation_loss=self._pyramid_translation_loss, consistency_loss=self._consistency_loss)
+        pyramid_num = len(pyramid_T_losses)
+        for i, (t_loss, r_loss) in enumerate(zip(pyramid_T_losses, pyramid_R_losses)):
+            pyramid_loss = pyramid_loss + self._pyloss_exp_w_base ** (pyramid_num - i) * (t_loss + r_loss)
+        loss = translation_loss + rotation_loss + pyramid_loss + C_loss
+        self.end_timer("Create_loss forward")
+        return {"loss": loss, "translation_loss": translation_loss.detach(), "rotation_loss": rotation_loss.detach(),
+                "pyramid_loss": pyramid_loss.detach(), "C_loss": C_loss.detach(),
+                "translation_preds": T_preds[0].detach(), "rotation_preds": R_preds[0].detach()}
+
+    def create_loss(self, preds_dict, example, translation_loss, rotation_loss, pyramid_translation_loss=None,
+                    pyramid_rotation_loss=None, pyramid_preds=None, consistency_loss=None):
+        translation_preds, rotation_preds = preds_dict["translation_preds"], preds_dict["rotation_preds"]
+        if not isinstance(translation_preds, (list, tuple)):
+            translation_preds = [translation_preds]
+        if not isinstance(rotation_preds, (list, tuple)):
+            rotation_preds = [rotation_preds]
+        dtype, device = translation_preds[0].dtype, translation_preds[0].device
+        pyramid_preds = preds_dict["pyramid_motion"]
+        step = self.get_global_step()
+        if "icp_odometry" in example:
+            icp = example["icp_odometry"].view(-1, 7)
+        else:                                   # the shipped dataset fills it with zeros (preprocess.py:618)
+            icp = torch.zeros((translation_preds[0].shape[0], 7), dtype=dtype, device=device)
+        translation_targets, rotation_targets = icp[:, :3], icp[:, 3:]
+        if translation_loss._loss_weight == 0:
+            self.warm_flag = True
+        if self.warm_flag:
+            warm_weight = 1.0 / (0.001 * step + 1) if step < 1500 else 0
+            translation_loss._loss_weight = warm_weight
+            rotation_loss._loss_weight = warm_weight
+        else:
+            warm_weight = 0
+
+        C_loss = torch.zeros([1], dtype=dtype, device=device)
+        res_r, res_t = None, None
+        if consistency_loss is not None:
+            assert len(preds_dict["middle_conf_preds"]) > 0
+            feats = preds_dict["voxel_features"]
+            cols = [0, 1, 2, 4, 5, 6] if feats[0].shape[1] > 6 else [0, 1, 2, 3, 4, 5]
+            points = [[p[:, cols][None]] for p in feats]
+            point_confs = [p[None] for p in preds_dict["middle_conf_preds"]]
+            min_len = min(p[0].shape[1] for p in points)                   # voxel_odom_net.py:646-651
+            points = [[p[0][:, :min_len]] for p in points]
+            point_confs = create_cycle_constraint_data([p[:, :min_len] for p in point_confs])
+            new_points = []
+            for h, _ in enumerate(points[0]):
+                new_points.append(create_cycle_constraint_data([points[t][h] for t in range(len(points))], 1))
+            if len(new_points) < len(rotation_preds):
+                new_points = new_points + [new_points[-1]] * (len(rotation_preds) - len(new_points))
+            else:
+                new_points = new_points[:len(rotation_preds)]
+            weights = [0.01, 0.01, 0.05, 0.1, 1]
+            for i, (R_pred, T_pred, weight) in enumerate(zip(rotation_preds, translation_preds,
+                                                             weights[-len(translation_preds):])):
+                if R_pred.shape[-1] == 9:
+                    R_pred = R_pred.reshape(-1, 3, 3)
+                else:
+                    R_pred = pose_utils.quaternion_to_rotation_matrix(roll(R_pred, shift=-1, dim=-1))
+                if step <= 1500:
+                    R_pred = torch.eye(3, device=device, dtype=dtype).expand(R_pred.shape[0], 3, 3).contiguous()
+                    T_pred = torch.zeros_like(T_pred)
+                p0, p1 = new_points[-(i + 1)][0], new_points[-(i + 1)][1]
+                transformed_p1_gt = p1[:, :, :3] @ R_pred.transpose(1, 2) + T_pred[:, None, :]
+                transformed_p1 = p0[:, :, :3]
+                transformed_normal1_gt = p1[:, :, 3:] @ R_pred.detach().transpose(1, 2)
+                transformed_normal1 = p0[:, :, 3:]
+                icp_iter = self.icp_iter if step > 1500 else 5
+                l, res_r, res_t = consistency_loss(
+                    transformed_p1, transformed_p1_gt, cov_pred=point_confs[0], cov_target=point_confs[1],
+                    R_pred=R_pred, t_pred=T_pred, normal_pred=transformed_normal1.detach(),
+                    normal_target=transformed_normal1_gt.detach(), mask=None, icp_iter=icp_iter)
+                C_loss = C_loss + (1 - warm_weight) * weight * l
+
+        if res_r is not None and res_t is not None:
+            rotation_targets = res_r @ R_pred.detach()
+            rotation_targets = pose_utils.rotation_matrix_to_quaternion(rotation_targets)
+            rotation_targets = roll(rotation_targets, 1, dim=-1)
+            rotation_targets = rotation_targets * torch.sign(rotation_targets[:, 0:1])
+            translation_targets = (res_r @ T_pred[..., None].detach() + res_t[..., None]).squeeze(-1)
+
+        if len(pyramid_preds) > 0:
+            tq_map_targets = self.gen_tq_maps(
+                torch.cat([translation_targets, rotation_targets], dim=-1).reshape(-1, 7),
+                spatial_size=pyramid_preds[-1][0].shape[2:], pc_range=self.odom_predictor.point_cloud_range,
+                cubic_tq_map=self.odom_predictor._cubic_pred_height > 0)
+            example["tq_maps"] = tq_map_targets
+        pyramid_targets = list(example["tq_maps"])
+
+        T_loss = 0
+        for p in translation_preds:
+            T_loss = T_loss + translation_loss(p, translation_targets)
+        R_loss = 0
+        for p in rotation_preds:
+            R_loss = R_loss + rotation_loss(p, rotation_targets)
+        if pyramid_translation_loss is None or pyramid_rotation_loss is None:
+            return T_loss, R_loss
+        pyramid_T_losses, pyramid_R_losses = [], []
+        for i, _ in enumerate(pyramid_preds):
+            T_pred_i, R_pred_i = pyramid_preds[i][0][:, :3], pyramid_preds[i][0][:, 3:]
+            pred_mask = pyramid_preds[i][1]
+            T_target, R_target = pyramid_targets[0][:, :3], pyramid_targets[0][:, 3:]
+            if T_target.shape != T_pred_i.shape:
+                T_target = F.interpolate(T_target, size=T_pred_i[0, 0].shape, mode="nearest")
+            if R_target.shape != R_pred_i.shape:
+                R_target = F.interpolate(R_target, size=T_pred_i[0, 0].shape, mode="nearest")
+            pyramid_T_losses.append(pyramid_translation_loss(T_pred_i, T_target, mask=pred_mask[:, :1]))
+            pyramid_R_losses.append(pyramid_rotation_loss(R_pred_i, R_target, mask=pred_mask[:, -1:]))
+        return T_loss, R_loss, pyramid_T_losses, pyramid_R_losses, C_loss

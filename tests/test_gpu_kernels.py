@@ -80,19 +80,19 @@ def _tables_gpu(K, coors4, n, shape):
     tab0 = K.site_table_build(coors4, n, shape)
     t["subm0"] = K.subm_table(coors4, n, tab0)
     tab1, c1, n1d, t["conv3d2"], t["conv3d2_inv"] = K.strided_table(coors4, n, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
-    n1 = int(n1d.item())
+    n1 = int(n1d[0].item())
     t["L1"] = (c1, n1, tab1)
     t["subm1"] = K.subm_table(c1, n1, tab1)
     tab2, c2, n2d, t["conv3d3"], t["conv3d3_inv"] = K.strided_table(c1, n1, tab1.shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
-    n2 = int(n2d.item())
+    n2 = int(n2d[0].item())
     t["L2"] = (c2, n2, tab2)
     t["subm2"] = K.subm_table(c2, n2, tab2)
     tab3, c3, n3d, t["conv3d4"], _ = K.strided_table(c2, n2, tab2.shape, (3, 3, 3), (2, 2, 2), (0, 1, 1))
-    n3 = int(n3d.item())
+    n3 = int(n3d[0].item())
     t["L3"] = (c3, n3, tab3)
     t["subm3"] = K.subm_table(c3, n3, tab3)
     tab4, c4, n4d, t["conv3d5"], _ = K.strided_table(c3, n3, tab3.shape, (3, 1, 1), (2, 1, 1), (0, 0, 0))
-    n4 = int(n4d.item())
+    n4 = int(n4d[0].item())
     t["L4"] = (c4, n4, tab4)
     return t
 
