@@ -30,6 +30,8 @@ typedef void* rslo_stream_t; /* cudaStream_t */
 
 int rslo_abi_version(void);
 const char* rslo_last_error(void);
+/* Kernels launched by this library in the calling process so far (measurement aid). */
+unsigned long long rslo_kernel_launch_count(void);
 
 /* ---- a10: exact nearest neighbour ---------------------------------------------------------------
  * Replaces cd.forward_cuda_one_direction (chamfer_distance.cpp:237-244 ->

@@ -134,6 +134,22 @@ def install():
     _installed = True
 
 
+def _patch_inplace_elu():
+    """middle.py:237 writes `features[:, :3] = F.elu(features[:, :3]) + ...` in place; under current
+    torch autograd rejects that (elu saved a view of the tensor being overwritten; torch 1.2 did not
+    check).  Give elu a private copy of its input inside that module only — same values, same grads."""
+    import types as _t
+
+    import torch.nn.functional as _F
+    from rslo.models import middle as _m
+    if getattr(_m.F, "_rslo_patched", False):
+        return
+    proxy = _t.SimpleNamespace(**{k: getattr(_F, k) for k in dir(_F) if not k.startswith("__")})
+    proxy.elu = lambda x, *a, **k: _F.elu(x.clone(), *a, **k)
+    proxy._rslo_patched = True
+    _m.F = proxy
+
+
 def build_reference_net(prototxt=None, testing=True, seed=7):
     """The reference's own builders on the reference's own prototxt -> (net, voxel_generator)."""
     install()
@@ -146,6 +162,7 @@ def build_reference_net(prototxt=None, testing=True, seed=7):
     with open(prototxt) as f:
         text_format.Merge(f.read(), cfg)
     vg = voxel_builder.build(cfg.model.second.voxel_generator)
+    _patch_inplace_elu()
     torch.manual_seed(seed)
     net = second_builder.build(cfg.model.second, vg, measure_time=False, testing=testing)
     return net, vg

@@ -21,6 +21,7 @@ _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
     "rslo_abi_version": (_i, []),
     "rslo_last_error": (C.c_char_p, []),
+    "rslo_kernel_launch_count": (C.c_ulonglong, []),
     "rslo_nn_workspace_bytes": (_sz, [_i, _i]),
     "rslo_nn_exact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "rslo_nn_brute": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp]),

@@ -10,6 +10,10 @@ namespace rslo {
 
 void set_last_error(const char* what, cudaError_t e);
 
+// Number of kernels this library has launched in the calling process (bench.py's gpu_launches).
+extern unsigned long long g_launch_count;
+#define RSLO_COUNT() (++::rslo::g_launch_count)
+
 #define RSLO_CHECK_LAUNCH(what)                              \
     do {                                                     \
         cudaError_t e__ = cudaGetLastError();                \

@@ -222,8 +222,10 @@ extern "C" int rslo_kabsch(const float* src, const float* tgt, const float* weig
     if (n > 0) {
         int blocks = cdiv(n, 256);
         if (blocks > 148 * 2) blocks = 148 * 2;
+        RSLO_COUNT();
         k_kabsch_accum<<<blocks, 256, 0, st>>>(src, tgt, weight, mask, dist, dist_threshold, n, acc);
     }
+    RSLO_COUNT();
     k_kabsch_solve<<<1, 32, 0, st>>>(acc, R_out, t_out, comp_R, comp_t);
     RSLO_CHECK_LAUNCH("rslo_kabsch");
     return 0;

@@ -5,6 +5,7 @@
 
 namespace rslo {
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 void set_last_error(const char* what, cudaError_t e)
 {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -13,3 +14,5 @@ void set_last_error(const char* what, cudaError_t e)
 
 extern "C" int rslo_abi_version(void) { return 1; }
 extern "C" const char* rslo_last_error(void) { return rslo::g_err; }
+
+extern "C" unsigned long long rslo_kernel_launch_count(void) { return rslo::g_launch_count; }

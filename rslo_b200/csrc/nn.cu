@@ -258,6 +258,7 @@ extern "C" int rslo_nn_brute(const float* query, int n, const float* target, int
         set_last_error("rslo_nn: empty target set", cudaErrorInvalidValue);
         return (int)cudaErrorInvalidValue;
     }
+    RSLO_COUNT();
     k_nn_brute<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(query, n, target, m, dist, idx);
     RSLO_CHECK_LAUNCH("rslo_nn_brute");
     return 0;
@@ -289,13 +290,19 @@ extern "C" int rslo_nn_exact(const float* query, int n, const float* target, int
     RSLO_CHECK(cudaMemsetAsync(fill, 0, (size_t)cap * sizeof(int), st));
     RSLO_CHECK(cudaMemsetAsync(bbox, 0x7f, 2 * sizeof(int), st));
     RSLO_CHECK(cudaMemsetAsync(bbox + 2, 0x80, 2 * sizeof(int), st));
+    RSLO_COUNT();
     k_nn_bbox<<<cdiv(m, 256), 256, 0, st>>>(target, m, bbox);
+    RSLO_COUNT();
     k_nn_params<<<1, 32, 0, st>>>(bbox, m, cap - 1, g);
+    RSLO_COUNT();
     k_nn_count<<<cdiv(m, 256), 256, 0, st>>>(target, m, g, cnt, cell_of_pt);
     int rc = scan_ints(cnt, start, cap, block_sums, nullptr, st);
     if (rc) return rc;
+    RSLO_COUNT();
     k_nn_fill<<<cdiv(m, 256), 256, 0, st>>>(target, m, cell_of_pt, start, fill, sorted);
+    RSLO_COUNT();
     k_nn_query<<<cdiv(n, 128), 128, 0, st>>>(query, n, g, start, sorted, dist, idx, fallback, g);
+    RSLO_COUNT();
     k_nn_fallback<<<148 * 2, 256, 0, st>>>(query, target, m, g, fallback, dist, idx);
     RSLO_CHECK_LAUNCH("rslo_nn_exact");
     return 0;

@@ -156,11 +156,16 @@ extern "C" int rslo_site_table_build(const int32_t* coors, int coor_stride, int 
         return (int)cudaErrorMemoryAllocation;
     }
     RSLO_CHECK(cudaMemsetAsync(cells, 0, nwords * sizeof(uint2), st));
-    if (n_cap > 0) k_site_mark<<<cdiv(n_cap, 256), 256, 0, st>>>(coors, coor_stride, n_cap, n_dev, H, W, cells);
+    if (n_cap > 0) {
+        RSLO_COUNT();
+        k_site_mark<<<cdiv(n_cap, 256), 256, 0, st>>>(coors, coor_stride, n_cap, n_dev, H, W, cells);
+    }
     int rc = scan_cells(cells, (int)nwords, block_sums, nullptr, st);
     if (rc) return rc;
-    if (perm && n_cap > 0)
+    if (perm && n_cap > 0) {
+        RSLO_COUNT();
         k_site_perm<<<cdiv(n_cap, 256), 256, 0, st>>>(coors, coor_stride, n_cap, n_dev, H, W, cells, perm);
+    }
     RSLO_CHECK_LAUNCH("rslo_site_table_build");
     return 0;
 }
@@ -171,6 +176,7 @@ extern "C" int rslo_subm_table(const int32_t* coors, int coor_stride, int n_cap,
 {
     if (n_cap <= 0) return 0;
     const int K = kd * kh * kw;
+    RSLO_COUNT();
     k_subm_table<<<cdiv((long long)n_cap * K, 256), 256, 0, (cudaStream_t)stream_>>>(
         coors, coor_stride, n_cap, n_dev, D, H, W, (const uint2*)cells, perm, kd, kh, kw, nbr);
     RSLO_CHECK_LAUNCH("rslo_subm_table");
@@ -206,12 +212,17 @@ extern "C" int rslo_strided_table(const int32_t* coors, int coor_stride, int n_c
         return 0;
     }
     const int G = cdiv((long long)n_cap * K, 256);
+    RSLO_COUNT();
     k_strided_mark<<<G, 256, 0, st>>>(coors, coor_stride, n_cap, n_dev, g, out_cells);
     int rc = scan_cells(out_cells, (int)nwords, block_sums, n_out_dev + 1, st);
     if (rc) return rc;
+    RSLO_COUNT();
     k_clamp_count<<<1, 32, 0, st>>>(n_out_dev, out_cap);
+    RSLO_COUNT();
     k_strided_coords<<<cdiv(nwords, 256), 256, 0, st>>>(out_cells, (int)nwords, g, out_cap, out_coors);
+    RSLO_COUNT();
     k_fill_rows<<<148 * 8, 256, 0, st>>>(nbr, K, out_cap, n_out_dev, -1);
+    RSLO_COUNT();
     k_strided_table<<<G, 256, 0, st>>>(coors, coor_stride, n_cap, n_dev, g, out_cells, out_cap, nbr, nbr_inv);
     RSLO_CHECK_LAUNCH("rslo_strided_table");
     return 0;

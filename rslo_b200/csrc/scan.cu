@@ -121,8 +121,11 @@ int scan_impl(Load ld, Store st, int n, int* block_sums, int* total_dev, cudaStr
         return 0;
     }
     const int nb = cdiv(n, SCAN_BLOCK);
+    RSLO_COUNT();
     k_scan_reduce<<<nb, SCAN_THREADS, 0, stream>>>(ld, n, block_sums);
+    RSLO_COUNT();
     k_scan_top<<<1, 1024, 0, stream>>>(block_sums, nb, total_dev);
+    RSLO_COUNT();
     k_scan_apply<<<nb, SCAN_THREADS, 0, stream>>>(ld, st, n, block_sums);
     RSLO_CHECK_LAUNCH("scan");
     return 0;

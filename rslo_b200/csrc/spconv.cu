@@ -216,6 +216,7 @@ int launch_fwd(const float* in, const int* nbr, int n_cap, const int* n_dev, int
     }
     const int grid = cdiv((long long)n_cap * 32, 256);
     bool handled = false;
+    RSLO_COUNT();
     RSLO_ALL_SHAPES((k_spconv_fwd<CI, CO><<<grid, 256, 0, st>>>(in, nbr, n_cap, n_dev, K, W, bias, scale,
                                                                shift, act, slope, out)))
     if (!handled) {
@@ -244,6 +245,7 @@ extern "C" int rslo_spconv_transpose_weight(const float* weight, int K, int Cin,
                                             float* weight_t, rslo_stream_t stream)
 {
     int tot = K * Cin * Cout;
+    RSLO_COUNT();
     k_transpose_w<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, Cin, Cout, mirror, weight_t);
     RSLO_CHECK_LAUNCH("rslo_spconv_transpose_weight");
     return 0;
@@ -267,6 +269,7 @@ extern "C" int rslo_spconv_backward_weight(const float* in, const float* grad_ou
     if (n_out_cap <= 0) return 0;
     dim3 grid(cdiv(n_out_cap, WG_ROWS), K);
     bool handled = false;
+    RSLO_COUNT();
     RSLO_ALL_SHAPES((k_spconv_wgrad<CI, CO><<<grid, 256, 0, st>>>(in, grad_out, nbr, n_out_cap, n_out_dev, K,
                                                                  grad_weight)))
     if (!handled) {
@@ -276,6 +279,7 @@ extern "C" int rslo_spconv_backward_weight(const float* in, const float* grad_ou
     if (grad_bias) {
         int blocks = cdiv(n_out_cap, 256 / Cout * 64);
         if (blocks > 148 * 4) blocks = 148 * 4;
+        RSLO_COUNT();
         k_colsum<<<blocks, 256, 0, st>>>(grad_out, n_out_cap, n_out_dev, Cout, grad_bias);
     }
     RSLO_CHECK_LAUNCH("rslo_spconv_backward_weight");
@@ -286,6 +290,7 @@ extern "C" int rslo_dense_from_sites(const float* feat, int C, const uint32_t* c
                                      int D, int H, int W, float* dense, rslo_stream_t stream)
 {
     int ncell = D * H * W;
+    RSLO_COUNT();
     k_dense<<<cdiv(ncell, 128), 128, 0, (cudaStream_t)stream>>>(feat, C, (const uint2*)cells, perm, ncell, dense);
     RSLO_CHECK_LAUNCH("rslo_dense_from_sites");
     return 0;
@@ -297,6 +302,7 @@ extern "C" int rslo_dense_backward(const float* grad_dense, int C, const int32_t
 {
     if (n_cap <= 0) return 0;
     int ncell = D * H * W;
+    RSLO_COUNT();
     k_dense_bwd<<<cdiv((long long)n_cap * C, 256), 256, 0, (cudaStream_t)stream>>>(
         grad_dense, C, coors, coor_stride, n_cap, n_dev, H, W, ncell, grad_feat);
     RSLO_CHECK_LAUNCH("rslo_dense_backward");

@@ -303,10 +303,13 @@ extern "C" int rslo_voxelize(const float* points, int P, int F, const float* vs,
     RSLO_CHECK(cudaMemsetAsync(first, 0x7f, (size_t)P * sizeof(int), st));
     RSLO_CHECK(cudaMemsetAsync(cnt, 0, (size_t)P * sizeof(int), st));
     RSLO_CHECK(cudaMemsetAsync(fill, 0, (size_t)P * sizeof(int), st));
+    RSLO_COUNT();
     k_vox_mark<<<GP, T, 0, st>>>(points, P, F, vp, keys, cells);
     int rc = scan_cells(cells, (int)nwords, block_sums, counters + 0, st);
     if (rc) return rc;
+    RSLO_COUNT();
     k_vox_first<<<GP, T, 0, st>>>(keys, P, cells, ranks, first, cnt);
+    RSLO_COUNT();
     k_vox_mark_first<<<GP, T, 0, st>>>(first, counters + 0, ptbits);
     rc = scan_cells(ptbits, (int)pwords, block_sums, counters + 1, st);
     if (rc) return rc;
@@ -317,19 +320,23 @@ extern "C" int rslo_voxelize(const float* points, int P, int F, const float* vs,
         RSLO_CHECK(cudaMemsetAsync(zmax, 0x80, (size_t)bw * bh * sizeof(int), st));   // < any real key
         RSLO_CHECK(cudaMemsetAsync(keep, 0, (size_t)max_voxels * sizeof(int), st));
     }
+    RSLO_COUNT();
     k_vox_scatter<<<GP, T, 0, st>>>(points, P, F, ranks, first, ptbits, offsets, fill, seg, max_voxels,
                                     keys, gx, gy, block_factor, bw, bh, zmin, zmax);
     if (filter) {
+        RSLO_COUNT();
         k_vox_filter<<<GP, T, 0, st>>>(counters + 0, first, ptbits, keys, max_voxels, gx, gy,
                                        block_factor, block_size, bw, bh, zmin, zmax, height_threshold,
                                        keep);
         rc = scan_ints(keep, newid, max_voxels, block_sums, counters + 2, st);
         if (rc) return rc;
     }
+    RSLO_COUNT();
     k_vox_gather<<<cdiv(P, 128), 128, 0, st>>>(points, F, counters + 0, first, ptbits, offsets, cnt, seg,
                                               keys, max_points, max_voxels, gx, gy, keep, newid,
                                               batch_idx, voxels, coors, coor_stride, num_points, mean,
                                               perm);
+    RSLO_COUNT();
     k_vox_count<<<1, 32, 0, st>>>(counters + 0, max_voxels, filter ? counters + 2 : nullptr,
                                   n_voxels_dev);
     RSLO_CHECK_LAUNCH("rslo_voxelize");
@@ -344,6 +351,7 @@ extern "C" int rslo_vfe_mean(const float* voxels, const int32_t* num_points, int
         set_last_error("rslo_vfe_mean: F < 7", cudaErrorInvalidValue);
         return (int)cudaErrorInvalidValue;
     }
+    RSLO_COUNT();
     k_vfe_mean<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(voxels, num_points, n, max_points, F, mean);
     RSLO_CHECK_LAUNCH("rslo_vfe_mean");
     return 0;

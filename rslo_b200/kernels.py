@@ -13,10 +13,68 @@ from . import _lib
 from ._lib import check, lib, ptr, stream, workspace
 
 LAUNCHES = {"calls": 0}
+PROFILE = None      # set to a list to record (name, start_event, end_event, algorithmic_bytes, flops) per call
 
 
 def _count(n=1):
     LAUNCHES["calls"] += n
+
+
+def kernel_launch_count():
+    """Kernels launched by librslo_b200 in this process (counted at the launch sites in csrc/)."""
+    return int(lib.rslo_kernel_launch_count())
+
+
+def _valid_entries(nbr):
+    """Rulebook size R of a table (cached on the tensor; profiling pass only)."""
+    r = getattr(nbr, "_rslo_R", None)
+    if r is None:
+        r = int((nbr >= 0).sum().item())
+        try:
+            nbr._rslo_R = r
+        except AttributeError:
+            pass
+    return r
+
+
+def _profiled(name, cost):
+    """When PROFILE is a list, bracket the call with CUDA events on the current stream and record
+    its algorithmic bytes / flops (SURVEY.md §8d formulas)."""
+    def deco(fn):
+        def wrapped(*a, **k):
+            if PROFILE is None:
+                return fn(*a, **k)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            nbytes, flops = cost(out, *a, **k)
+            PROFILE.append((name, s, e, nbytes, flops))
+            return out
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
+def _cost_spconv(out, feat, nbr, n_out, weight, *a, **k):
+    Kk = nbr.shape[1]
+    cin, cout = weight.shape[-2], weight.shape[-1]
+    R = _valid_entries(nbr)
+    return 4 * (feat.shape[0] * cin + n_out * cout + Kk * cin * cout) + 8 * R, 2 * R * cin * cout
+
+
+def _cost_spconv_bwd_data(out, grad_out, nbr_t, n_in, weight, mirror):
+    Kk = nbr_t.shape[1]
+    cin, cout = weight.shape[-2], weight.shape[-1]
+    R = _valid_entries(nbr_t)
+    return 4 * (grad_out.shape[0] * cout + n_in * cin + Kk * cin * cout) + 8 * R, 2 * R * cin * cout
+
+
+def _cost_spconv_bwd_weight(out, feat, grad_out, nbr, n_out, weight_shape, need_bias=True):
+    Kk = nbr.shape[1]
+    cin, cout = weight_shape[-2], weight_shape[-1]
+    R = _valid_entries(nbr)
+    return 4 * (feat.shape[0] * cin + n_out * cout + Kk * cin * cout) + 8 * R, 2 * R * cin * cout
 
 
 def _i32(t):
@@ -36,6 +94,7 @@ def _nwords(D, H, W):
 # ------------------------------------------------------------------------------------------------
 # a10: nearest neighbour
 # ------------------------------------------------------------------------------------------------
+@_profiled("nn_exact", lambda out, q, t, brute=False: (12 * (q.shape[0] + t.shape[0]) + 8 * q.shape[0], 0))
 def nn_exact(query, target, brute=False):
     """query [n,3], target [m,3] f32 cuda -> (dist [n] f32, idx [n] i32).  Bit-identical to the
     reference ChamferDistanceKernel (thirdparty/chamfer_distance/chamfer_distance.cu:6-137)."""
@@ -82,6 +141,8 @@ def site_table_build(coors, n, shape, n_dev=None, need_perm=True):
     return SiteTable((D, H, W), cells, perm)
 
 
+@_profiled("subm_table", lambda out, coors, n, table, ksize=(3, 3, 3), n_dev=None:
+           (16 * n + 4 * n * int(np.prod(ksize)) + 8 * _nwords(*table.shape), 0))
 def subm_table(coors, n, table, ksize=(3, 3, 3), n_dev=None):
     coors = _i32(coors)
     D, H, W = table.shape
@@ -98,6 +159,8 @@ def out_shape_of(shape, ksize, stride, pad):
     return tuple((int(s) + 2 * p - k) // st + 1 for s, k, st, p in zip(shape, ksize, stride, pad))
 
 
+@_profiled("strided_table", lambda out, coors, n, shape, ksize, *a, **k:
+           (16 * n + 16 * out[1].shape[0] + 4 * (n + out[1].shape[0]) * int(np.prod(ksize)), 0))
 def strided_table(coors, n, shape, ksize, stride, pad, n_dev=None, out_cap=None):
     """-> (out_table, out_coors [cap,4], n_out_dev [2] i32 {clamped, raw}, nbr [cap,K], nbr_inv [n,K])."""
     coors = _i32(coors)
@@ -126,6 +189,9 @@ def strided_table(coors, n, shape, ksize, stride, pad, n_dev=None, out_cap=None)
 # ------------------------------------------------------------------------------------------------
 # voxeliser
 # ------------------------------------------------------------------------------------------------
+@_profiled("voxelize", lambda out, points, *a, **k:
+           (points.numel() * 4 + (28 + 16) * out["coordinates"].shape[0] +
+            (0 if out["voxels"] is None else out["voxels"].numel() * 4), 0))
 def voxelize(points, voxel_size, pc_range, grid_size, max_points=10, max_voxels=40000, block_factor=1,
              block_size=8, height_threshold=-1.0, batch_idx=0, materialize=True, with_mean=True,
              with_table=False, coor_stride=4):
@@ -175,6 +241,7 @@ def vfe_mean(voxels, num_points):
 # ------------------------------------------------------------------------------------------------
 # sparse convolution
 # ------------------------------------------------------------------------------------------------
+@_profiled("spconv_forward", _cost_spconv)
 def spconv_forward(feat, nbr, n_out, weight, bias=None, scale=None, shift=None, act=0, slope=0.01,
                    n_out_dev=None):
     feat = _f32(feat)
@@ -193,6 +260,7 @@ def spconv_forward(feat, nbr, n_out, weight, bias=None, scale=None, shift=None, 
     return out
 
 
+@_profiled("spconv_backward_data", _cost_spconv_bwd_data)
 def spconv_backward_data(grad_out, nbr_t, n_in, weight, mirror):
     g = _f32(grad_out.contiguous())
     nbr_t = _i32(nbr_t)
@@ -210,6 +278,7 @@ def spconv_backward_data(grad_out, nbr_t, n_in, weight, mirror):
     return grad_in
 
 
+@_profiled("spconv_backward_weight", _cost_spconv_bwd_weight)
 def spconv_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=True):
     feat = _f32(feat)
     g = _f32(grad_out.contiguous())
@@ -225,6 +294,7 @@ def spconv_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=T
     return gw, gb
 
 
+@_profiled("dense_from_sites", lambda out, feat, table: (feat.numel() * 4 + out.numel() * 4, 0))
 def dense_from_sites(feat, table):
     feat = _f32(feat)
     D, H, W = table.shape
@@ -251,6 +321,7 @@ def dense_backward(grad_dense, coors, n, shape, C_):
 # ------------------------------------------------------------------------------------------------
 # a12: weighted Kabsch
 # ------------------------------------------------------------------------------------------------
+@_profiled("kabsch", lambda out, src, *a, **k: (src.shape[0] * 4 * (3 + 3 + 1 + 1), 0))
 def kabsch(src, tgt, weight=None, mask=None, dist=None, dist_threshold=None, comp_R=None, comp_t=None):
     """src/tgt [n,3] -> (R [3,3], t [3]) with SVDHead's return convention (rslo/layers/svd.py:57-64).
     Sync-free: selection by `mask` and/or `dist < dist_threshold` happens inside the reduction."""

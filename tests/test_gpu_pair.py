@@ -1,0 +1,148 @@
+"""End-to-end parity of the CUDA hot path (net(example) through the C-ABI kernels) against
+  (1) the golden fixtures produced by the REFERENCE network (tests/golden/make_golden.py), and
+  (2) the CPU oracle (oracle/net.py) on the same seeded inputs.
+Tolerance (north_star): integer outputs bit-exact; pose and loss 1e-4 relative fp32.  Gradients are
+checked at 2e-3 of the tensor's max magnitude (fp32 accumulation order over ~1e4..1e5 terms differs
+between the atomics-free CUDA reduction and torch's CPU index_add)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net as onet
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden as mg  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def net(cuda):
+    import rslo_b200
+    n, vg = rslo_b200.build_network(testing=True, seed=7)
+    return n.cuda(), vg
+
+
+def _prep(net, name):
+    g = np.load(os.path.join(GOLDEN, f"pair_{name}.npz"))
+    seed, beams, n_az, T, step, wseed = (int(v) for v in g["meta"])
+    onet.fill_weights(net, wseed)
+    net.global_step.fill_(step)
+    net._step_host = None
+    frames = mg.make_frames(seed, beams, n_az, T)
+    return g, frames, step
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.mark.parametrize("name", ["small_eval", "full_eval"])
+def test_eval_matches_reference_golden(net, name):
+    net, vg = net
+    g, frames, _ = _prep(net, name)
+    net.eval()
+    with torch.no_grad():
+        out = net({"points": [torch.from_numpy(f).cuda() for f in frames]})
+    assert [int(v.shape[0]) for v in out["voxel_features"]] == g["n_voxels"].tolist()       # bit-exact counts
+    pose = torch.cat([out["translation_preds"], out["rotation_preds"]], -1).cpu().numpy()
+    np.testing.assert_allclose(pose, g["pose"], rtol=1e-4, atol=1e-5)
+    assert _rel(out["tq_map_g"][:, :, ::8, ::8].cpu().numpy(), g["tq_map_g_sample"]) < 1e-4
+    assert _rel(out["t_conf"][:, :, ::8, ::8].cpu().numpy(), g["t_conf_sample"]) < 1e-4
+    assert _rel(out["middle_conf_preds"][0][::97].cpu().numpy(), g["cov0_sample"]) < 1e-4
+    assert _rel(out["tq_map_g"].abs().sum(dim=(1, 2, 3)).cpu().numpy(), g["tq_map_g_abs_sum"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["small_train", "small_train_warm", "small_train_t3"])
+def test_train_matches_reference_golden(net, name):
+    net, vg = net
+    g, frames, _ = _prep(net, name)
+    net.train()
+    net.zero_grad()
+    ret = net({"points": [torch.from_numpy(f).cuda() for f in frames], "host_outputs": False})
+    ret["loss"].sum().backward()
+    pose = torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1).cpu().numpy()
+    np.testing.assert_allclose(pose, g["pose"], rtol=1e-4, atol=1e-5)
+    for k in ("translation_loss", "rotation_loss", "pyramid_loss", "C_loss", "loss"):
+        np.testing.assert_allclose(ret[k].detach().cpu().numpy().reshape(-1), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+    params = dict(net.named_parameters())
+    for k in mg.GRAD_KEYS:
+        ref = g["grad:" + k]
+        got = params[k].grad
+        if ref.size == 0:
+            assert got is None
+            continue
+        assert _rel(mg.grad_sample(got.cpu().numpy()), ref) < 2e-3, k
+
+
+def test_reference_style_example_matches_points_path(net):
+    """The reference's input contract (voxels / num_points / coordinates made by the voxel
+    generator) and the fused raw-points path give identical outputs."""
+    net, vg = net
+    g, frames, _ = _prep(net, "small_eval")
+    net.eval()
+    ex = {"voxels": [], "num_points": [], "coordinates": [], "num_voxels": []}
+    for f in frames:
+        r = vg.generate(f, 40000)
+        n = len(r["coordinates"])
+        assert r["coordinates"].shape == (n, 3) and r["voxels"].shape == (n, 10, 7)
+        ex["voxels"].append(torch.from_numpy(r["voxels"]).cuda())
+        ex["num_points"].append(torch.from_numpy(r["num_points_per_voxel"]).cuda())
+        ex["coordinates"].append(torch.from_numpy(np.concatenate([np.zeros((n, 1), np.int32), r["coordinates"]], 1)).cuda())
+        ex["num_voxels"].append(torch.tensor([[n]], dtype=torch.int64))
+    with torch.no_grad():
+        a = net(ex)
+        b = net({"points": [torch.from_numpy(f).cuda() for f in frames]})
+    assert torch.equal(a["translation_preds"], b["translation_preds"])
+    assert torch.equal(a["rotation_preds"], b["rotation_preds"])
+    pose = torch.cat([a["translation_preds"], a["rotation_preds"]], -1).cpu().numpy()
+    np.testing.assert_allclose(pose, g["pose"], rtol=1e-4, atol=1e-5)
+
+
+def test_pair_matches_oracle_other_seed(net):
+    """A pair no fixture covers: CUDA path vs the CPU oracle run on the box."""
+    net, vg = net
+    from rslo_b200.data import synthetic
+    a, b, _ = synthetic.make_pair(5, n_beams=24, n_az=500)
+    onet.fill_weights(net, 21)
+    net.global_step.fill_(5000)
+    net._step_host = None
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ref = onet.pair_forward(sd, [a, b], training=True, step=5000)
+    net.train()
+    ret = net({"points": [torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()], "host_outputs": False})
+    pose = torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1).cpu().numpy()
+    np.testing.assert_allclose(pose, ref["pose"], rtol=1e-4, atol=1e-5)
+    for k in ("translation_loss", "rotation_loss", "pyramid_loss", "C_loss", "loss"):
+        np.testing.assert_allclose(ret[k].detach().cpu().numpy().reshape(-1), ref[k].reshape(-1), rtol=1e-4,
+                                   atol=1e-5, err_msg=k)
+
+
+def test_loss_stack_on_oracle_inputs(net):
+    """Loss stack alone (a10-a14) fed with the oracle's own intermediate tensors, so the NN
+    association sees bit-identical inputs: every term within 1e-4 relative, residual pose 1e-5."""
+    net, vg = net
+    from rslo_b200.data import synthetic
+    a, b, _ = synthetic.make_pair(3, n_beams=32, n_az=900)
+    onet.fill_weights(net, 31)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ref = onet.pair_forward(sd, [a, b], training=True, step=3000)
+    feats, covs = ref["voxel_features"], ref["cov"]
+    n = min(f.shape[0] for f in feats)
+    from rslo_b200.utils import pose_utils
+    q = torch.from_numpy(ref["pose"][:, 3:]).cuda()
+    t = torch.from_numpy(ref["pose"][:, :3]).cuda()
+    R = pose_utils.quaternion_to_rotation_matrix(torch.roll(q, -1, -1))
+    p0, p1 = feats[0][:n].cuda(), feats[1][:n].cuda()
+    tgt = p1[None, :, :3] @ R.transpose(1, 2) + t[:, None, :]
+    l, res_r, res_t = net._consistency_loss(p0[None, :, :3], tgt, cov_pred=covs[0][:n][None].cuda(),
+                                            cov_target=covs[1][:n][None].cuda(), R_pred=R, t_pred=t,
+                                            normal_pred=p0[None, :, [4, 5, 6]], normal_target=None, icp_iter=2)
+    np.testing.assert_allclose(l.detach().cpu().numpy().reshape(-1), ref["C_loss"].reshape(-1), rtol=1e-4)
+    np.testing.assert_allclose(res_r.cpu().numpy(), ref["res_r"], atol=1e-5)
+    np.testing.assert_allclose(res_t.cpu().numpy(), ref["res_t"], atol=1e-5)
