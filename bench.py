@@ -277,7 +277,12 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = K.kernel_launch_count()
+    cuda_prof = os.environ.get("RSLO_BENCH_CUDA_PROFILER") == "1"      # ncu --profile-from-start off
+    if cuda_prof:
+        torch.cuda.profiler.start()
     ms = timed(args.steps, False, W)
+    if cuda_prof:
+        torch.cuda.profiler.stop()
     launches = K.kernel_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     value = world * ppg * args.steps / (ms / 1e3)
