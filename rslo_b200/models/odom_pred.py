@@ -10,6 +10,8 @@ entries, tests/golden/state_dict_shapes.json).  Differences that do not change a
   * cell-anchor grids are cached instead of rebuilt per call.
 The 2-D convolutions are dense contractions and run through cuDNN in FP32.
 """
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -76,6 +78,23 @@ def _conf_stack(cin, BN, ReLU):
     return nn.Sequential(nn.Conv2d(cin, 64, kernel_size=3, padding=1), BN(64), ReLU(),
                          nn.Conv2d(64, 32, kernel_size=3, padding=1), BN(32), ReLU(),
                          nn.Conv2d(32, 1, kernel_size=1))
+
+
+class _FlatHead(nn.Module):
+    """Tensor-in / tensor-out view of the head for CUDA-graph capture (shares the head's parameters;
+    never registered as a child, so state_dict keys are unchanged)."""
+
+    def __init__(self, head, n_levels):
+        super().__init__()
+        self.head = head
+        self.n_levels = n_levels
+
+    def forward(self, *bevs):
+        d = self.head._forward(list(bevs))
+        out = [d["translation_preds"][0], d["rotation_preds"][0], d["tq_map_g"], d["t_conf"], d["r_conf"]]
+        for pred, mask in d["pyramid_motion"]:
+            out += [pred, mask]
+        return tuple(out)
 
 
 @register_odom_pred
@@ -200,8 +219,39 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
         return [torch.stack(x1, dim=1).reshape(-1, C, H, W), torch.stack(x2, dim=1).reshape(-1, C, H, W)]
 
     def forward(self, xs, tq_map_gt=None, local_spatial_features=None, **kwargs):
+        if not isinstance(xs, list):
+            xs = [xs]
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=HEAD_ALLOW_TF32):
+            if self.use_cuda_graph and xs[0].is_cuda and self.dense_predict and self.pred_pyramid_motion:
+                return self._forward_graphed(xs)
             return self._forward(xs, tq_map_gt, local_spatial_features, **kwargs)
+
+    # ---- CUDA-graph replay of the head -----------------------------------------------------------
+    # Every shape in the head is fixed by the BEV grid, so forward and backward are each captured
+    # once per (frames, mode) into a CUDA graph (torch.cuda.make_graphed_callables) and replayed:
+    # ~2000 small cuDNN / elementwise launches per step become two graph launches.
+    use_cuda_graph = os.environ.get("RSLO_CUDA_GRAPHS", "1") != "0"
+
+    def _forward_graphed(self, xs):
+        key = (len(xs), self.training, tuple(x.requires_grad for x in xs), tuple(xs[0].shape), xs[0].device.index)
+        cache = self.__dict__.setdefault("_graphed", {})
+        g = cache.get(key)
+        if g is None:
+            flat = _FlatHead(self, len(self.deblocks))
+            flat.training = self.training
+            bufs = {n: b.clone() for n, b in self.named_buffers()}
+            sample = tuple(torch.randn_like(x).requires_grad_(x.requires_grad) for x in xs)
+            with torch.enable_grad():
+                g = torch.cuda.make_graphed_callables(flat, sample, allow_unused_input=True)
+            with torch.no_grad():                      # capture warm-up ran BN on the random sample
+                for n, b in self.named_buffers():
+                    b.copy_(bufs[n])
+            cache[key] = g
+        outs = g(*[x.contiguous() for x in xs])
+        t, q, tq_map_g, t_conf, r_conf = outs[:5]
+        pyramid = [[outs[5 + 2 * i], outs[6 + 2 * i]] for i in range((len(outs) - 5) // 2)]
+        return {"translation_preds": [t], "rotation_preds": [q], "tq_map_g": tq_map_g, "pyramid_motion": pyramid,
+                "transformed_inputs": None, "t_conf": t_conf, "r_conf": r_conf}
 
     def _forward(self, xs, tq_map_gt=None, local_spatial_features=None, **kwargs):
         if not isinstance(xs, list):
