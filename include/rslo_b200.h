@@ -122,6 +122,20 @@ int rslo_spconv_backward_weight(const float* in, const float* grad_out, const in
                                 int n_out_cap, const int32_t* n_out_dev, int K, int Cin, int Cout,
                                 float* grad_weight, float* grad_bias, rslo_stream_t stream);
 
+/* Tensor-core variant for Cin, Cout in {32, 64} (csrc/spconv_tc.cu): tcgen05.mma kind::tf32 with a
+ * 3xTF32 operand split (FP32-level accuracy), TMEM accumulator, weight tiles staged by bulk async copy.
+ * `image` is the pre-swizzled {hi, lo} weight image made by rslo_spconv_tc_prepare
+ * (rslo_spconv_tc_image_bytes bytes): transpose = 0 for the forward filter bank (kdim = Cin, ndim = Cout),
+ * transpose = 1 (+ mirror for submanifold tables) for the data gradient (kdim = Cout, ndim = Cin).
+ * rslo_spconv_tc_forward computes out[o,:] = act(bias + sum_k in[nbr[o,k],:] @ B_k), in [.,kdim], out [.,ndim]. */
+int rslo_spconv_tc_supported(int Cin, int Cout, int K);
+size_t rslo_spconv_tc_image_bytes(int K, int Cin, int Cout);
+int rslo_spconv_tc_prepare(const float* weight, int K, int Cin, int Cout, int transpose, int mirror,
+                           float* image, rslo_stream_t stream);
+int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n_out_cap, const int32_t* n_out_dev,
+                           int K, int kdim, int ndim, const float* image, const float* bias, int act,
+                           float slope, float* out, rslo_stream_t stream);
+
 /* ---- a7: SparseConvTensor.dense() + view (middle.py:240-243) ------------------------------------
  * feat [n,C] at sites of a (D,H,W) level -> dense [C*D, H, W] f32 (zero where no site). */
 int rslo_dense_from_sites(const float* feat, int C, const uint32_t* cells, const int32_t* perm,
@@ -133,17 +147,36 @@ int rslo_dense_backward(const float* grad_dense, int C, const int32_t* coors, in
 
 /* ---- a12: weighted Kabsch alignment (no host round trip) -----------------------------------------
  * Replaces SVDHead.forward (rslo/layers/svd.py:13-64) as driven by the ICP refinement in
- * rslo/core/losses.py:440-488.  src/tgt [n,3] f32 row-major; weight [n] or NULL (ones); mask [n]
+ * rslo/core/losses.py:440-488.  src [n,3], tgt rows f32 row-major; tgt_idx [n] or NULL: row i pairs with
+ * tgt[tgt_idx[i]] (the association gather); weight [n] or NULL (ones); normal [n,3] or NULL: when given the
+ * weight is multiplied by cos^2(normal_i, tgt_i - src_i) (losses.py:411); mask [n]
  * 0/1 floats or NULL; optional ROI test dist[i] < *dist_threshold (both device, may be NULL).
  * Means are unweighted over the selected points, H = sum m w (x-xbar)(y-ybar)^T, R = V U^T with the
  * det<0 reflection fix; writes the reference's return values R_out = R^T [9], t_out = -R^T t [3].
  * comp_R [9] / comp_t [3] (may be NULL) are updated in place as comp_R <- R_out comp_R,
  * comp_t <- R_out comp_t + t_out (losses.py:463-465). */
 size_t rslo_kabsch_workspace_bytes(void);
-int rslo_kabsch(const float* src, const float* tgt, const float* weight, const float* mask,
-                const float* dist, const float* dist_threshold, int n, float* R_out, float* t_out,
-                float* comp_R, float* comp_t, void* workspace, size_t workspace_bytes,
+int rslo_kabsch(const float* src, const float* tgt, const int32_t* tgt_idx, const float* weight,
+                const float* normal, const float* mask, const float* dist, const float* dist_threshold, int n,
+                float* R_out, float* t_out, float* comp_R, float* comp_t, void* workspace, size_t workspace_bytes,
                 rslo_stream_t stream);
+
+/* ---- a11: covariance-weighted residual of the consistency loss (losses.py:348-363, 401-435) --------
+ * pred [n,3], target [m,3], idx [n] (association into target), cov_pred [n,7], cov_target [m,7] raw
+ * covariance parameters (3 eigenvalue increments + quaternion x,y,z,w), R [9] detached predicted rotation,
+ * ROI = dist[i] < *dist_threshold.  loss = mean_roi(d^T S^-1 d) + reg * mean_roi(0.5 log det S),
+ * S = C(cov_pred[i]) + R C(cov_target[idx[i]]) R^T.  sums: 4 doubles of scratch that the backward reads
+ * (sum, logdet sum, ROI count).  Backward writes grad_pred [n,3] (may be NULL), grad_cov_pred [n,7] and
+ * accumulates grad_target [m,3], grad_cov_target [m,7] (zeroed inside). */
+int rslo_cov_residual_forward(const float* pred, const float* target, const int32_t* idx, const float* cov_pred,
+                              const float* cov_target, const float* R, const float* dist,
+                              const float* dist_threshold, int n, float reg_weight, double* sums, float* loss,
+                              rslo_stream_t stream);
+int rslo_cov_residual_backward(const float* pred, const float* target, const int32_t* idx, const float* cov_pred,
+                               const float* cov_target, const float* R, const float* dist,
+                               const float* dist_threshold, int n, int m, float reg_weight, const double* sums,
+                               const float* grad_loss, float* grad_pred, float* grad_target, float* grad_cov_pred,
+                               float* grad_cov_target, rslo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -3,9 +3,9 @@
 The consistency loss is restated without host round trips: where the reference compacts the ROI
 points with boolean-mask indexing (a `nonzero` sync per use, `losses.py:416-420,441-447`), branches
 on `det < 0` and wraps `torch.inverse` in try/except, this version keeps all N points and applies
-the ROI as a 0/1 factor inside the reductions — the same sums over the same points — and uses
-closed-form 3x3 inverse / determinant.  Nearest neighbours come from csrc/nn.cu, the ICP alignment
-from csrc/kabsch.cu.
+the ROI as a predicate inside the reductions — the same sums over the same points.  Nearest
+neighbours come from csrc/nn.cu, the covariance-weighted residual (forward and backward) from
+csrc/cov_residual.cu, the ICP alignment from csrc/kabsch.cu.
 """
 import torch
 from torch import nn
@@ -57,33 +57,6 @@ class AdaptiveWeightedL2Loss(Loss):
         return loss.sum() + _alpha
 
 
-def span_cov2(cov_param_pred):
-    """7 raw parameters -> 3x3 covariance V diag(l1, l1+l2, l1+l2+l3) V^T (`losses.py:348-363`)."""
-    p = cov_param_pred
-    l1 = p[:, 0:1]
-    l2 = l1 + p[:, 1:2]
-    l3 = l2 + p[:, 2:3]
-    q = p[:, 3:] / (torch.norm(p[:, 3:], dim=-1, keepdim=True) + 1e-9)
-    eigvec = pose_utils.quaternion_to_rotation_matrix(q)          # (x,y,z,w), as the reference feeds it
-    lam = torch.cat([l1, l2, l3], dim=1)
-    return (eigvec * lam[:, None, :]) @ eigvec.transpose(-1, -2)
-
-
-def inv_det_3x3(m):
-    """Closed-form inverse and determinant of a batch of 3x3 matrices."""
-    a, b, c = m[:, 0, 0], m[:, 0, 1], m[:, 0, 2]
-    d, e, f = m[:, 1, 0], m[:, 1, 1], m[:, 1, 2]
-    g, h, i = m[:, 2, 0], m[:, 2, 1], m[:, 2, 2]
-    A = e * i - f * h
-    B = -(d * i - f * g)
-    Cc = d * h - e * g
-    det = a * A + b * B + c * Cc
-    adj = torch.stack([A, -(b * i - c * h), b * f - c * e,
-                       B, a * i - c * g, -(a * f - c * d),
-                       Cc, -(a * h - b * g), a * e - b * d], dim=-1).view(-1, 3, 3)
-    return adj / det[:, None, None], det
-
-
 class Aleat5_1ChamferL2NormalWeightedALLSVDLoss(Loss):
     """`losses.py:301-507`: NN association, Mahalanobis residual under the summed predicted
     covariances + log-det regulariser, then `icp_iter` rounds of normal-weighted Kabsch refinement
@@ -127,41 +100,25 @@ class Aleat5_1ChamferL2NormalWeightedALLSVDLoss(Loss):
             src = xyz_pred[b].detach().contiguous()
             tgt_full = xyz_target[b].detach().contiguous()
             dist, idx = K.nn_exact(src, tgt_full)
-            idxl = idx.long()
-            xyz_assoc = xyz_target[b][idxl]
             thr = self._roi_threshold(dist)
-            roi = dist < thr
-            cnt = roi.sum().to(xyz_pred.dtype)
+            # Mahalanobis residual under the summed covariances + log-det regulariser, ROI mean:
+            # one fused kernel forward, one backward (csrc/cov_residual.cu)
+            loss = loss + K.cov_residual(xyz_pred[b], xyz_target[b], cov_pred[b], cov_target[b], R_pred[b].detach(),
+                                         idx, dist, thr, self.reg_weight)
 
-            cov_p = span_cov2(cov_pred[b])
-            cov_t = span_cov2(cov_target[b])[idxl]
-            Rb = R_pred[b].detach()
-            sigma = cov_p + Rb @ cov_t @ Rb.transpose(-1, -2)
-            # rows outside the ROI do not enter the loss: neutralise them BEFORE the nonlinear ops so
-            # neither their values nor their gradients can produce inf/nan
-            sigma = torch.where(roi[:, None, None], sigma, eye)
-            diff_vec = torch.where(roi[:, None], xyz_pred[b] - xyz_assoc, torch.zeros_like(xyz_assoc))
-            sigma_inv, det = inv_det_3x3(sigma)
-            square_diff = (diff_vec[:, None, :] @ sigma_inv @ diff_vec[:, :, None]).view(-1)
-            logdet = torch.where(roi, 0.5 * torch.log(det), torch.zeros_like(det))
-            loss_ = square_diff.sum() / cnt + self.reg_weight * (logdet.sum() / cnt)
-            loss = loss + loss_
-
-            # ICP refinement on detached points (losses.py:440-488)
+            # ICP refinement on detached points (losses.py:440-488): the association gather, the
+            # |cos(normal, q - p)|^2 weight and the ROI test all happen inside the Kabsch reduction
             with torch.no_grad():
-                nrm = normal_pred[b].detach()
-                wgt = F.cosine_similarity(nrm, xyz_assoc.detach() - src, dim=-1).abs()
+                nrm = normal_pred[b].detach().contiguous()
                 res_r_ = eye.clone()
                 res_t_ = torch.zeros(3, device=src.device, dtype=src.dtype)
-                cur_tgt, cur_dist, cur_thr = xyz_assoc.detach().contiguous(), dist, thr
+                cur_rows, cur_idx, cur_dist, cur_thr = tgt_full, idx, dist, thr
                 for icp_i in range(icp_iter):
-                    K.kabsch(src, cur_tgt, weight=(wgt * wgt).contiguous(), dist=cur_dist,
-                             dist_threshold=cur_thr, comp_R=res_r_, comp_t=res_t_)
+                    K.kabsch(src, cur_rows, tgt_idx=cur_idx, normal=nrm, dist=cur_dist, dist_threshold=cur_thr,
+                             comp_R=res_r_, comp_t=res_t_)
                     if icp_i < icp_iter - 1:
-                        moved = tgt_full @ res_r_.t() + res_t_
-                        cur_dist, i2 = K.nn_exact(src, moved)
-                        cur_tgt = moved[i2.long()]
-                        wgt = F.cosine_similarity(nrm, cur_tgt - src, dim=-1).abs()
+                        cur_rows = torch.addmm(res_t_, tgt_full, res_r_.t())
+                        cur_dist, cur_idx = K.nn_exact(src, cur_rows)
                         cur_thr = self._roi_threshold(cur_dist)
             res_R.append(res_r_[None])
             res_T.append(res_t_[None])

@@ -19,9 +19,9 @@ namespace {
 constexpr int KB_NACC = 26;  // m, mx(3), my(3), mw, mwx(3), mwy(3), mwxy(9), pad -> 26 used: 1+3+3+1+3+3+9 = 23
 
 __global__ void __launch_bounds__(256)
-k_kabsch_accum(const float* __restrict__ src, const float* __restrict__ tgt, const float* __restrict__ weight,
-               const float* __restrict__ mask, const float* __restrict__ dist, const float* __restrict__ thr,
-               int n, double* __restrict__ acc)
+k_kabsch_accum(const float* __restrict__ src, const float* __restrict__ tgt, const int* __restrict__ tgt_idx,
+               const float* __restrict__ weight, const float* __restrict__ normal, const float* __restrict__ mask,
+               const float* __restrict__ dist, const float* __restrict__ thr, int n, double* __restrict__ acc)
 {
     double a[23];
 #pragma unroll
@@ -31,9 +31,21 @@ k_kabsch_accum(const float* __restrict__ src, const float* __restrict__ tgt, con
         float m = mask ? mask[i] : 1.f;
         if (dist) m = dist[i] < th ? m : 0.f;          // ROI: dist < threshold (losses.py:331)
         if (m == 0.f) continue;
-        const double w = weight ? (double)weight[i] : 1.0;
-        const double x[3] = {src[i * 3], src[i * 3 + 1], src[i * 3 + 2]};
-        const double y[3] = {tgt[i * 3], tgt[i * 3 + 1], tgt[i * 3 + 2]};
+        const int ti = tgt_idx ? tgt_idx[i] : i;                 // association gather fused (losses.py:405,476)
+        const float xf[3] = {src[i * 3], src[i * 3 + 1], src[i * 3 + 2]};
+        const float yf[3] = {tgt[(size_t)ti * 3], tgt[(size_t)ti * 3 + 1], tgt[(size_t)ti * 3 + 2]};
+        double w = weight ? (double)weight[i] : 1.0;
+        if (normal) {
+            // w = |cos(normal_i, y - x)|^2 (losses.py:411,440-456: cosine_similarity(...).abs(), squared at the call)
+            const float nx = normal[i * 3], ny = normal[i * 3 + 1], nz = normal[i * 3 + 2];
+            const float vx = yf[0] - xf[0], vy = yf[1] - xf[1], vz = yf[2] - xf[2];
+            const float nn = fmaxf(sqrtf(nx * nx + ny * ny + nz * nz), 1e-8f);
+            const float vn = fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-8f);
+            const float c = (nx * vx + ny * vy + nz * vz) / (nn * vn);
+            w *= (double)(c * c);
+        }
+        const double x[3] = {xf[0], xf[1], xf[2]};
+        const double y[3] = {yf[0], yf[1], yf[2]};
         const double dm = m, mw = dm * w;
         a[0] += dm;
         a[7] += mw;
@@ -207,10 +219,10 @@ using namespace rslo;
 
 extern "C" size_t rslo_kabsch_workspace_bytes(void) { return 32 * sizeof(double); }
 
-extern "C" int rslo_kabsch(const float* src, const float* tgt, const float* weight, const float* mask,
-                           const float* dist, const float* dist_threshold, int n, float* R_out, float* t_out,
-                           float* comp_R, float* comp_t, void* workspace, size_t workspace_bytes,
-                           rslo_stream_t stream)
+extern "C" int rslo_kabsch(const float* src, const float* tgt, const int32_t* tgt_idx, const float* weight,
+                           const float* normal, const float* mask, const float* dist, const float* dist_threshold,
+                           int n, float* R_out, float* t_out, float* comp_R, float* comp_t, void* workspace,
+                           size_t workspace_bytes, rslo_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (workspace_bytes < 32 * sizeof(double)) {
@@ -223,7 +235,7 @@ extern "C" int rslo_kabsch(const float* src, const float* tgt, const float* weig
         int blocks = cdiv(n, 256);
         if (blocks > 148 * 2) blocks = 148 * 2;
         RSLO_COUNT();
-        k_kabsch_accum<<<blocks, 256, 0, st>>>(src, tgt, weight, mask, dist, dist_threshold, n, acc);
+        k_kabsch_accum<<<blocks, 256, 0, st>>>(src, tgt, tgt_idx, weight, normal, mask, dist, dist_threshold, n, acc);
     }
     RSLO_COUNT();
     k_kabsch_solve<<<1, 32, 0, st>>>(acc, R_out, t_out, comp_R, comp_t);

@@ -77,27 +77,28 @@ __global__ void k_transpose_w(const float* __restrict__ W, int K, int Cin, int C
 // dW[k] += sum over rows o of a chunk with nbr[o,k] >= 0 of in[nbr[o,k],:]^T (x) g[o,:]
 // grid (chunks, K); 256 threads; each thread owns Cin*Cout/256 (>=1) accumulators.
 constexpr int WG_ROWS = 1024;  // rows per chunk
-constexpr int WG_TILE = 32;    // valid rows staged per step
+constexpr int WG_TILE = 64;    // valid rows staged per step
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 k_spconv_wgrad(const float* __restrict__ in, const float* __restrict__ g, const int* __restrict__ nbr,
                int n_cap, const int* n_dev, int K, float* __restrict__ dW)
 {
-    constexpr int NE = (CIN * COUT + 255) / 256;       // elements per thread
+    // register tile per thread: TM input channels x TN output channels on a fixed 16 x 16 thread grid
+    constexpr int TM = CIN >= 64 ? 4 : (CIN >= 32 ? 2 : 1);
+    constexpr int TN = COUT >= 64 ? 4 : (COUT >= 32 ? 2 : 1);
     __shared__ int s_list_o[WG_ROWS];
     __shared__ int s_list_j[WG_ROWS];
     __shared__ int s_count;
-    __shared__ float s_a[WG_TILE][CIN];
-    __shared__ float s_g[WG_TILE][COUT];
+    __shared__ __align__(16) float s_a[WG_TILE][CIN];
+    __shared__ __align__(16) float s_g[WG_TILE][COUT];
     const int n = dev_count(n_dev, n_cap);
     const int k = blockIdx.y;
     const int row0 = blockIdx.x * WG_ROWS;
     if (row0 >= n) return;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    // compact the chunk's valid (o, j) pairs (order within the chunk is irrelevant to the sum's
-    // value only up to fp32 rounding; we keep row order per warp ballot for reproducibility)
+    // compact the chunk's valid (o, j) pairs
     for (int base = 0; base < WG_ROWS; base += 256) {
         int o = row0 + base + threadIdx.x;
         int j = (o < n) ? __ldg(nbr + (size_t)o * K + k) : -1;
@@ -114,9 +115,14 @@ k_spconv_wgrad(const float* __restrict__ in, const float* __restrict__ g, const 
     }
     __syncthreads();
     const int cnt = s_count;
-    float acc[NE];
+    if (cnt == 0) return;
+    const int ci0 = (threadIdx.x >> 4) * TM, co0 = (threadIdx.x & 15) * TN;
+    const bool active = ci0 < CIN && co0 < COUT;
+    float acc[TM][TN];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) acc[e] = 0.f;
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
     for (int base = 0; base < cnt; base += WG_TILE) {
         const int m = min(WG_TILE, cnt - base);
         for (int t = threadIdx.x; t < m * CIN; t += 256) {
@@ -128,23 +134,28 @@ k_spconv_wgrad(const float* __restrict__ in, const float* __restrict__ g, const 
             s_g[r][c] = __ldg(g + (size_t)s_list_o[base + r] * COUT + c);
         }
         __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int r = 0; r < m; ++r) {
+                float av[TM], gv[TN];
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            int idx = threadIdx.x + e * 256;
-            if (idx < CIN * COUT) {
-                int ci = idx / COUT, co = idx % COUT;
-                float s = acc[e];
-                for (int r = 0; r < m; ++r) s = fmaf(s_a[r][ci], s_g[r][co], s);
-                acc[e] = s;
+                for (int a = 0; a < TM; ++a) av[a] = s_a[r][ci0 + a];
+#pragma unroll
+                for (int b = 0; b < TN; ++b) gv[b] = s_g[r][co0 + b];
+#pragma unroll
+                for (int a = 0; a < TM; ++a)
+#pragma unroll
+                    for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], gv[b], acc[a][b]);
             }
         }
         __syncthreads();
     }
-    if (cnt == 0) return;
+    if (active) {
 #pragma unroll
-    for (int e = 0; e < NE; ++e) {
-        int idx = threadIdx.x + e * 256;
-        if (idx < CIN * COUT) atomicAdd(dW + (size_t)k * CIN * COUT + idx, acc[e]);
+        for (int a = 0; a < TM; ++a)
+#pragma unroll
+            for (int b = 0; b < TN; ++b)
+                atomicAdd(dW + ((size_t)k * CIN + ci0 + a) * COUT + co0 + b, acc[a][b]);
     }
 }
 

@@ -1,0 +1,383 @@
+// K4-TC: sparse 3-D convolution as an implicit GEMM on the 5th-gen tensor cores (sm_100a, tcgen05).
+//
+//   out[o,:] = act(bias + sum_k in[nbr[o,k],:] @ W[k])        Cin, Cout in {32, 64}
+//
+// One CTA owns 128 output rows (one TMEM lane per row) and the full Cout.  For every kernel offset
+// k that at least one of its rows uses, the producer warps gather the 128 neighbour rows (zeros
+// where a row has no neighbour) into shared memory in the UMMA canonical K-major SWIZZLE_128B
+// layout, while the offset's weight tile arrives by one bulk async copy (TMA unit, cp.async.bulk)
+// from a pre-swizzled image.  A single elected thread issues tcgen05.mma (kind::tf32, M=128,
+// N=Cout, K=8) into a TMEM accumulator; the epilogue reads it back with tcgen05.ld, applies
+// bias + LeakyReLU and writes the rows.
+//
+// FP32 fidelity (the path's parity bound is 1e-4 relative, which plain TF32 misses): split-TF32.
+// Each operand is split as x ~= hi + lo with hi = RN_tf32(x) and lo = RN_tf32(x - hi) (x - hi is
+// exact in fp32), so the pair represents x to 2^-23 relative — fp32's own precision — and all four
+// products hi*hi + lo*hi + hi*lo + lo*lo are accumulated in the FP32 TMEM accumulator.  The splits
+// are made while staging (A) / in the weight prep kernel (B), so the tensor core only ever sees
+// operands that are already TF32-exact (no dependence on how the hardware would round).
+//
+// Pipeline: 2 shared-memory stages; full[s] (producers + bulk-copy tx -> MMA), empty[s]
+// (tcgen05.commit -> producers), acc (last commit -> epilogue).
+#include "common.cuh"
+
+namespace rslo {
+namespace {
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_STAGES = 2;
+constexpr int TC_PRODUCERS = 128;          // warps 0..3: gather, then epilogue
+constexpr int TC_THREADS = 160;            // + warp 4: TMEM owner and MMA issuer
+constexpr unsigned TC_SPIN_LIMIT = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a broken pipeline traps (sticky launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    for (unsigned spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spin > TC_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows are 128 B (32 fp32), 8-row groups are
+// 1024 B apart (SBO), LBO = 1 (unused by swizzled K-major), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of element (row, col) inside a [rows x KDIM] fp32 operand stored as KDIM/32 blocks of
+// [rows x 32] in the canonical K-major SWIZZLE_128B layout
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows)
+{
+    const int kb = col >> 5, c16 = (col & 31) >> 2, r8 = row & 7;
+    return (uint32_t)kb * (uint32_t)(rows * 128) + (uint32_t)(row >> 3) * 1024u + (uint32_t)r8 * 128u +
+           (uint32_t)((c16 ^ r8) << 4) + (uint32_t)(col & 3) * 4u;
+}
+
+// round-to-nearest (ties away) onto TF32's 10-bit mantissa; the carry may ripple into the exponent
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+// ---- weight prep: W [K,Cin,Cout] -> per-offset images {B_hi, B_lo}, B is [NDIM x KDIM] K-major ----
+//   forward      (transpose = 0): NDIM = Cout, KDIM = Cin,  B(n, kk) = W[k][kk][n]
+//   data-grad    (transpose = 1): NDIM = Cin,  KDIM = Cout, B(n, kk) = W[ks][n][kk], ks = mirror ? K-1-k : k
+__global__ void k_tc_prep(const float* __restrict__ W, int K, int Cin, int Cout, int transpose, int mirror,
+                          float* __restrict__ img)
+{
+    const int NDIM = transpose ? Cin : Cout, KDIM = transpose ? Cout : Cin;
+    const int per = NDIM * KDIM;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= K * per) return;
+    const int k = t / per, e = t % per, n = e / KDIM, kk = e % KDIM;
+    float v;
+    if (!transpose) v = W[((size_t)k * Cin + kk) * Cout + n];
+    else v = W[((size_t)(mirror ? K - 1 - k : k) * Cin + n) * Cout + kk];
+    const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
+    char* base = (char*)img + (size_t)k * per * 8;
+    const uint32_t off = sw128_offset(n, kk, NDIM);
+    *(float*)(base + off) = hi;
+    *(float*)(base + (size_t)per * 4 + off) = lo;
+}
+
+template <int KDIM, int NDIM>
+struct TcSmem {
+    static constexpr int A_BYTES = TC_ROWS * KDIM * 4;             // one of {hi, lo}
+    static constexpr int B_BYTES = NDIM * KDIM * 4;                // one of {hi, lo}
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int NBR_BYTES = TC_ROWS * 32 * 4;             // K <= 32
+    static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + NBR_BYTES + 256 + 1024;   // + barriers + alignment slack
+};
+
+template <int KDIM, int NDIM>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap, const int* n_dev, int K,
+            const float* __restrict__ bimg, const float* __restrict__ bias, int act, float slope,
+            float* __restrict__ out)
+{
+    using S = TcSmem<KDIM, NDIM>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    int* s_nbr = (int*)(smem + TC_STAGES * S::STAGE_BYTES);
+    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * S::STAGE_BYTES + S::NBR_BYTES);
+    uint64_t* full_bar = bars;                // [TC_STAGES]
+    uint64_t* empty_bar = bars + TC_STAGES;   // [TC_STAGES]
+    uint64_t* acc_bar = bars + 2 * TC_STAGES;
+    uint32_t* s_tmem = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+    uint32_t* s_mask = s_tmem + 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = dev_count(n_dev, n_cap);
+    const int row0 = blockIdx.x * TC_ROWS;
+    if (row0 >= n) return;                    // uniform per CTA
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full_bar + s, TC_PRODUCERS);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(acc_bar, 1);
+        *s_mask = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        constexpr int COLS = NDIM < 32 ? 32 : NDIM;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    // neighbour tile -> smem, and the set of offsets this tile uses
+    unsigned my_mask = 0;
+    for (int i = tid; i < TC_ROWS * K; i += TC_THREADS) {
+        const int r = i / K, k = i - r * K;
+        const int o = row0 + r;
+        const int v = o < n ? __ldg(nbr + (size_t)o * K + k) : -1;
+        s_nbr[i] = v;
+        if (v >= 0) my_mask |= 1u << k;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) my_mask |= __shfl_xor_sync(0xffffffffu, my_mask, d);
+    if (lane == 0 && my_mask) atomicOr(s_mask, my_mask);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned mask = *s_mask;
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp < 4) {
+        // ================= producers =================
+        constexpr int CHUNKS = KDIM / 4;                 // 16-byte chunks per row
+        constexpr int ROWS_PER_LD = 32 / CHUNKS;         // rows covered by one warp-wide load
+        const int sub = lane / CHUNKS, c = lane % CHUNKS;
+        unsigned m = mask;
+        for (int it = 0; m; ++it) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(empty_bar + s, ph ^ 1);
+            uint8_t* stage = smem + s * S::STAGE_BYTES;
+            if (tid == 0) {
+                mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                bulk_copy_g2s(stage + 2 * S::A_BYTES, (const char*)bimg + (size_t)k * 2 * S::B_BYTES, 2 * S::B_BYTES,
+                              full_bar + s);
+            }
+            uint8_t* a_hi = stage;
+            uint8_t* a_lo = stage + S::A_BYTES;
+#pragma unroll 4
+            for (int j = 0; j < 32 / ROWS_PER_LD; ++j) {
+                const int r = warp * 32 + j * ROWS_PER_LD + sub;
+                const int src = s_nbr[r * K + k];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src >= 0) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM) + c);
+                float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                float4 l = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
+                const uint32_t off = sw128_offset(r, c * 4, TC_ROWS);
+                *reinterpret_cast<float4*>(a_hi + off) = h;
+                *reinterpret_cast<float4*>(a_lo + off) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+            mbar_arrive(full_bar + s);
+        }
+        // ================= epilogue =================
+        const int o = row0 + warp * 32 + lane;
+        float acc[NDIM];
+        if (mask) {
+            mbar_wait(acc_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int cb = 0; cb < NDIM; cb += 16) tmem_ld16(taddr + cb, acc + cb);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NDIM; ++i) acc[i] = 0.f;
+        }
+        if (o < n) {
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)o * NDIM);
+#pragma unroll
+            for (int i = 0; i < NDIM; i += 4) {
+                float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                if (bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + i));
+                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                }
+                if (act == 1) {
+                    v.x = v.x > 0.f ? v.x : v.x * slope;
+                    v.y = v.y > 0.f ? v.y : v.y * slope;
+                    v.z = v.z > 0.f ? v.z : v.z * slope;
+                    v.w = v.w > 0.f ? v.w : v.w * slope;
+                }
+                dst[i / 4] = v;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ================= MMA issuer (one elected lane of warp 4) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(NDIM);
+            unsigned m = mask;
+            uint32_t first = 1;
+            for (int it = 0; m; ++it) {
+                m &= m - 1;
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(full_bar + s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + S::A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
+                const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                for (int part = 0; part < 4; ++part) {                 // lo*lo, lo*hi, hi*lo, hi*hi
+                    const uint32_t a = (part & 2) ? a_hi : a_lo;
+                    const uint32_t b = (part & 1) ? b_hi : b_lo;
+#pragma unroll
+                    for (int kb = 0; kb < KDIM / 32; ++kb)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t ad = umma_desc_k_sw128(a + kb * (TC_ROWS * 128) + kk * 32);
+                            const uint64_t bd = umma_desc_k_sw128(b + kb * (NDIM * 128) + kk * 32);
+                            umma_tf32(tmem_base, ad, bd, idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                }
+                umma_commit(empty_bar + s);            // frees the stage when these MMAs retire
+            }
+            if (mask) umma_commit(acc_bar);            // accumulator complete -> epilogue
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        constexpr int COLS = NDIM < 32 ? 32 : NDIM;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+    }
+}
+
+template <int KDIM, int NDIM>
+int launch_tc(const float* in, const int* nbr, int n_cap, const int* n_dev, int K, const float* bimg,
+              const float* bias, int act, float slope, float* out, cudaStream_t st)
+{
+    using S = TcSmem<KDIM, NDIM>;
+    static bool configured = false;
+    if (!configured) {
+        RSLO_CHECK(cudaFuncSetAttribute(k_spconv_tc<KDIM, NDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured = true;
+    }
+    RSLO_COUNT();
+    k_spconv_tc<KDIM, NDIM><<<cdiv(n_cap, TC_ROWS), TC_THREADS, S::TOTAL, st>>>(in, nbr, n_cap, n_dev, K, bimg, bias, act,
+                                                                              slope, out);
+    RSLO_CHECK_LAUNCH("rslo_spconv_tc");
+    return 0;
+}
+
+}  // namespace
+}  // namespace rslo
+
+using namespace rslo;
+
+extern "C" int rslo_spconv_tc_supported(int Cin, int Cout, int K)
+{
+    return (Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64) && K >= 1 && K <= 32;
+}
+
+extern "C" size_t rslo_spconv_tc_image_bytes(int K, int Cin, int Cout) { return (size_t)K * Cin * Cout * 8; }
+
+extern "C" int rslo_spconv_tc_prepare(const float* weight, int K, int Cin, int Cout, int transpose, int mirror,
+                                      float* image, rslo_stream_t stream)
+{
+    if (!rslo_spconv_tc_supported(Cin, Cout, K)) {
+        set_last_error("rslo_spconv_tc_prepare: unsupported shape", cudaErrorInvalidValue);
+        return (int)cudaErrorInvalidValue;
+    }
+    const int tot = K * Cin * Cout;
+    RSLO_COUNT();
+    k_tc_prep<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, Cin, Cout, transpose, mirror, image);
+    RSLO_CHECK_LAUNCH("rslo_spconv_tc_prepare");
+    return 0;
+}
+
+extern "C" int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n_out_cap, const int32_t* n_out_dev,
+                                      int K, int kdim, int ndim, const float* image, const float* bias, int act,
+                                      float slope, float* out, rslo_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_out_cap <= 0) return 0;
+    if (K < 1 || K > 32) {
+        set_last_error("rslo_spconv_tc_forward: K must be in 1..32", cudaErrorInvalidValue);
+        return (int)cudaErrorInvalidValue;
+    }
+    if (kdim == 64 && ndim == 64) return launch_tc<64, 64>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
+    if (kdim == 64 && ndim == 32) return launch_tc<64, 32>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
+    if (kdim == 32 && ndim == 64) return launch_tc<32, 64>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
+    if (kdim == 32 && ndim == 32) return launch_tc<32, 32>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
+    set_last_error("rslo_spconv_tc_forward: unsupported (kdim, ndim)", cudaErrorInvalidValue);
+    return (int)cudaErrorInvalidValue;
+}

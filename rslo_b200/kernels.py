@@ -260,6 +260,42 @@ def spconv_forward(feat, nbr, n_out, weight, bias=None, scale=None, shift=None, 
     return out
 
 
+def spconv_tc_supported(Cin, Cout, K):
+    return bool(lib.rslo_spconv_tc_supported(int(Cin), int(Cout), int(K)))
+
+
+def spconv_tc_prepare(weight, transpose=False, mirror=False):
+    """W [K,Cin,Cout] -> pre-swizzled 3xTF32 {hi, lo} image for csrc/spconv_tc.cu."""
+    w = _f32(weight.contiguous())
+    Kk, Cin, Cout = w.shape[-3] if w.dim() == 3 else w.numel() // (w.shape[-2] * w.shape[-1]), w.shape[-2], w.shape[-1]
+    img = torch.empty(Kk * Cin * Cout * 2, dtype=torch.float32, device=w.device)
+    check(lib.rslo_spconv_tc_prepare(ptr(w), Kk, Cin, Cout, 1 if transpose else 0, 1 if mirror else 0, ptr(img),
+                                     stream()), "rslo_spconv_tc_prepare")
+    _count()
+    return img
+
+
+def _cost_spconv_tc(out, feat, nbr, n_out, image, kdim, ndim, *a, **k):
+    Kk = nbr.shape[1]
+    R = _valid_entries(nbr)
+    return 4 * (feat.shape[0] * kdim + n_out * ndim + Kk * kdim * ndim) + 8 * R, 2 * R * kdim * ndim
+
+
+@_profiled("spconv_tc", _cost_spconv_tc)
+def spconv_tc_forward(feat, nbr, n_out, image, kdim, ndim, bias=None, act=0, slope=0.01, n_out_dev=None):
+    """out[o,:] = act(bias + sum_k feat[nbr[o,k],:] @ B_k) on tcgen05 tensor cores (3xTF32)."""
+    feat = _f32(feat)
+    nbr = _i32(nbr)
+    assert feat.shape[1] == kdim
+    out = torch.empty((n_out, ndim), dtype=torch.float32, device=feat.device)
+    if n_out == 0:
+        return out
+    check(lib.rslo_spconv_tc_forward(ptr(feat), ptr(nbr), n_out, ptr(n_out_dev), nbr.shape[1], kdim, ndim, ptr(image),
+                                     ptr(bias), act, float(slope), ptr(out), stream()), "rslo_spconv_tc_forward")
+    _count()
+    return out
+
+
 @_profiled("spconv_backward_data", _cost_spconv_bwd_data)
 def spconv_backward_data(grad_out, nbr_t, n_in, weight, mirror):
     g = _f32(grad_out.contiguous())
@@ -322,16 +358,62 @@ def dense_backward(grad_dense, coors, n, shape, C_):
 # a12: weighted Kabsch
 # ------------------------------------------------------------------------------------------------
 @_profiled("kabsch", lambda out, src, *a, **k: (src.shape[0] * 4 * (3 + 3 + 1 + 1), 0))
-def kabsch(src, tgt, weight=None, mask=None, dist=None, dist_threshold=None, comp_R=None, comp_t=None):
-    """src/tgt [n,3] -> (R [3,3], t [3]) with SVDHead's return convention (rslo/layers/svd.py:57-64).
-    Sync-free: selection by `mask` and/or `dist < dist_threshold` happens inside the reduction."""
+def kabsch(src, tgt, weight=None, mask=None, dist=None, dist_threshold=None, comp_R=None, comp_t=None, tgt_idx=None,
+           normal=None):
+    """src [n,3], tgt rows -> (R [3,3], t [3]) with SVDHead's return convention (rslo/layers/svd.py:57-64).
+    Sync-free: selection by `mask` and/or `dist < dist_threshold`, the association gather (`tgt_idx`) and
+    the normal-cosine weight (`normal`) all happen inside the reduction."""
     src = _f32(src.contiguous())
     tgt = _f32(tgt.contiguous())
     n = src.shape[0]
     R = torch.empty((3, 3), dtype=torch.float32, device=src.device)
     t = torch.empty(3, dtype=torch.float32, device=src.device)
     ws = workspace(lib.rslo_kabsch_workspace_bytes(), "kabsch")
-    check(lib.rslo_kabsch(ptr(src), ptr(tgt), ptr(weight), ptr(mask), ptr(dist), ptr(dist_threshold), n, ptr(R),
-                          ptr(t), ptr(comp_R), ptr(comp_t), ptr(ws), ws.numel(), stream()), "rslo_kabsch")
+    check(lib.rslo_kabsch(ptr(src), ptr(tgt), ptr(tgt_idx), ptr(weight), ptr(normal), ptr(mask), ptr(dist),
+                          ptr(dist_threshold), n, ptr(R), ptr(t), ptr(comp_R), ptr(comp_t), ptr(ws), ws.numel(),
+                          stream()), "rslo_kabsch")
     _count()
     return R, t
+
+
+# ------------------------------------------------------------------------------------------------
+# a11: covariance-weighted residual (fused forward / backward)
+# ------------------------------------------------------------------------------------------------
+class _CovResidualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, cov_pred, cov_target, R, idx, dist, thr, reg):
+        pred, target = _f32(pred.contiguous()), _f32(target.contiguous())
+        cov_pred, cov_target = _f32(cov_pred.contiguous()), _f32(cov_target.contiguous())
+        R = _f32(R.contiguous())
+        n = pred.shape[0]
+        sums = torch.empty(4, dtype=torch.float64, device=pred.device)
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        check(lib.rslo_cov_residual_forward(ptr(pred), ptr(target), ptr(idx), ptr(cov_pred), ptr(cov_target), ptr(R),
+                                            ptr(dist), ptr(thr), n, float(reg), ptr(sums), ptr(loss), stream()),
+              "rslo_cov_residual_forward")
+        _count()
+        ctx.save_for_backward(pred, target, cov_pred, cov_target, R, idx, dist, thr, sums)
+        ctx.reg = float(reg)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, cov_pred, cov_target, R, idx, dist, thr, sums = ctx.saved_tensors
+        g = _f32(g.contiguous())
+        n, m = pred.shape[0], target.shape[0]
+        g_pred = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
+        g_t = torch.empty_like(target)
+        g_cp = torch.empty_like(cov_pred)
+        g_ct = torch.empty((m, 7), dtype=torch.float32, device=pred.device)
+        check(lib.rslo_cov_residual_backward(ptr(pred), ptr(target), ptr(idx), ptr(cov_pred), ptr(cov_target), ptr(R),
+                                             ptr(dist), ptr(thr), n, m, ctx.reg, ptr(sums), ptr(g), ptr(g_pred),
+                                             ptr(g_t), ptr(g_cp), ptr(g_ct), stream()), "rslo_cov_residual_backward")
+        _count()
+        return g_pred, g_t, g_cp, g_ct, None, None, None, None, None
+
+
+def cov_residual(pred, target, cov_pred, cov_target, R, idx, dist, thr, reg_weight):
+    """mean_roi(d^T S^-1 d) + reg * mean_roi(0.5 log det S) -> [1]; differentiable w.r.t. pred, target,
+    cov_pred, cov_target (rslo/core/losses.py:348-363, 401-435)."""
+    return _CovResidualFn.apply(pred, target, cov_pred, cov_target, R, _i32(idx), _f32(dist), _f32(thr.reshape(1)),
+                                reg_weight)

@@ -7,6 +7,7 @@ Compute is the output-stationary gather-convolution kernel (csrc/spconv.cu) over
 by csrc/rulebook.cu; there is no PyTorch or CPU fallback.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -66,6 +67,11 @@ class SparseConvTensor:
         return out.view(1, self.features.shape[1], D, H, W)
 
 
+# Layers with Cin, Cout in {32, 64} can run on the tcgen05 tensor-core kernel (csrc/spconv_tc.cu,
+# split-TF32); the narrow layers (7/16 channels) stay on the FP32 FFMA kernel.
+USE_TC = os.environ.get("RSLO_SPCONV_TC", "0") == "1"
+
+
 class _DenseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, st, C_):
@@ -88,7 +94,13 @@ class _SpConvFn(torch.autograd.Function):
         nbr = entry.nbr_t if inverse else entry.nbr
         n_out = entry.n_in if inverse else entry.n_out
         feat = feat.contiguous()
-        out = K.spconv_forward(feat, nbr, n_out, weight, bias, act=act, slope=slope)
+        Kk, Cin, Cout = weight.shape
+        ctx.tc = USE_TC and K.spconv_tc_supported(Cin, Cout, Kk)
+        if ctx.tc:
+            img = K.spconv_tc_prepare(weight)
+            out = K.spconv_tc_forward(feat, nbr, n_out, img, Cin, Cout, bias, act=act, slope=slope)
+        else:
+            out = K.spconv_forward(feat, nbr, n_out, weight, bias, act=act, slope=slope)
         ctx.entry, ctx.inverse, ctx.act, ctx.slope = entry, inverse, act, slope
         ctx.has_bias = bias is not None
         ctx.save_for_backward(feat, weight, out if act else None)
@@ -107,7 +119,12 @@ class _SpConvFn(torch.autograd.Function):
         n_in = e.n_out if inverse else e.n_in
         gi = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gi = K.spconv_backward_data(g, nbr_t, n_in, weight, e.mirror)
+            if ctx.tc:
+                Kk, Cin, Cout = weight.shape
+                img_t = K.spconv_tc_prepare(weight, transpose=True, mirror=e.mirror)
+                gi = K.spconv_tc_forward(g, nbr_t, n_in, img_t, Cout, Cin)
+            else:
+                gi = K.spconv_backward_data(g, nbr_t, n_in, weight, e.mirror)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = K.spconv_backward_weight(feat, g, nbr, n_out, weight.shape, need_bias=ctx.has_bias)
         return gi, gw, gb, None, None, None, None

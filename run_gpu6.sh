@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/pytest_all.log
+grep -E "^E  |FAILED|passed|failed|Error" gpurun_out/pytest_all.log | head -50
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err
+cat gpurun_out/bench.log; tail -3 gpurun_out/bench.err

@@ -223,3 +223,99 @@ def test_nn_bit_exact(K, scan_pair, n, m, kind):
     if r is not None:   # pin oracle AND kernel against the reference's own CUDA kernel
         assert np.array_equal(r[1].cpu().numpy(), i_ref)
         assert np.array_equal(r[0].cpu().numpy(), d_ref)
+
+
+@pytest.mark.parametrize("cin,cout,K_", [(64, 64, 27), (32, 32, 27), (32, 64, 27), (64, 32, 27), (64, 64, 3)])
+def test_spconv_tensor_core_forward(K, cin, cout, K_):
+    """tcgen05 3xTF32 implicit-GEMM kernel vs the oracle's gather-conv: FP32-level agreement."""
+    g = torch.Generator().manual_seed(cin * 100 + cout + K_)
+    n_in, n_out = 3000, 2500 + 77            # not a multiple of the 128-row tile
+    nbr = torch.randint(0, n_in, (n_out, K_), generator=g, dtype=torch.int32)
+    nbr[torch.rand((n_out, K_), generator=g) < 0.6] = -1
+    nbr[128:256] = -1                        # a whole tile without any neighbour -> bias only
+    nbr[300:428, 1:] = -1                    # a tile that uses a single offset
+    feat = torch.randn((n_in, cin), generator=g)
+    w = torch.randn((K_, cin, cout), generator=g) * 0.1
+    b = torch.randn(cout, generator=g)
+    ref = torch.nn.functional.leaky_relu(osp.gather_conv(feat, nbr, w, b), 0.01)
+    img = K.spconv_tc_prepare(w.cuda())
+    out = K.spconv_tc_forward(feat.cuda(), nbr.cuda(), n_out, img, cin, cout, b.cuda(), act=1, slope=0.01)
+    torch.cuda.synchronize()
+    # 3xTF32: ~1e-5 relative (tensor-core accumulation is not full IEEE fp32); the path bound is 1e-4
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=5e-5, atol=1e-4)
+    # data gradient through the transposed image == FFMA data-gradient kernel == autograd
+    go = torch.randn((n_out, cout), generator=g)
+    n_t = 2000
+    nbr_t = torch.randint(0, n_out, (n_t, K_), generator=g, dtype=torch.int32)
+    nbr_t[torch.rand((n_t, K_), generator=g) < 0.6] = -1
+    for mirror in (False, True):
+        img_t = K.spconv_tc_prepare(w.cuda(), transpose=True, mirror=mirror)
+        gi = K.spconv_tc_forward(go.cuda(), nbr_t.cuda(), n_t, img_t, cout, cin)
+        gi_ref = K.spconv_backward_data(go.cuda(), nbr_t.cuda(), n_t, w.cuda(), mirror)
+        np.testing.assert_allclose(gi.cpu().numpy(), gi_ref.cpu().numpy(), rtol=5e-5, atol=1e-4)
+
+
+def _span_cov2_torch(p):
+    """losses.py:348-363 with torch ops (test-side restatement, runs on the GPU through autograd)."""
+    from oracle import quat
+    l1 = p[:, 0:1]
+    l2 = l1 + p[:, 1:2]
+    l3 = l2 + p[:, 2:3]
+    q = p[:, 3:] / (torch.norm(p[:, 3:], dim=-1, keepdim=True) + 1e-9)
+    V = quat.quaternion_to_rotation_matrix(q)
+    lam = torch.cat([l1, l2, l3], dim=1)
+    return (V * lam[:, None, :]) @ V.transpose(-1, -2)
+
+
+def test_cov_residual_matches_torch_autograd(K):
+    """Fused covariance-residual kernel (forward + backward) vs the same math composed from torch ops
+    (torch.inverse / torch.det, boolean-mask ROI) differentiated by autograd."""
+    g = torch.Generator().manual_seed(3)
+    n, m = 5000, 4700
+    pred = (torch.randn(n, 3, generator=g) * 10).cuda().requires_grad_(True)
+    tgt = (torch.randn(m, 3, generator=g) * 10).cuda().requires_grad_(True)
+    idx = torch.randint(0, m, (n,), generator=g, dtype=torch.int32).cuda()
+    cp = torch.randn(n, 7, generator=g)
+    ct = torch.randn(m, 7, generator=g)
+    cp[:, :3] = torch.rand(n, 3, generator=g) * 0.5 + 0.05
+    ct[:, :3] = torch.rand(m, 3, generator=g) * 0.5 + 0.05
+    cp, ct = cp.cuda().requires_grad_(True), ct.cuda().requires_grad_(True)
+    ang = torch.tensor(0.3)
+    R = torch.tensor([[torch.cos(ang), -torch.sin(ang), 0], [torch.sin(ang), torch.cos(ang), 0], [0, 0, 1.0]]).cuda()
+    dist = torch.rand(n, generator=g).cuda() * 3
+    thr = torch.tensor([2.0]).cuda()
+    loss = K.cov_residual(pred, tgt, cp, ct, R, idx, dist, thr, 0.005)
+    (loss.sum() * 1.7).backward()
+    got = [loss.detach().clone(), pred.grad.clone(), tgt.grad.clone(), cp.grad.clone(), ct.grad.clone()]
+    for t in (pred, tgt, cp, ct):
+        t.grad = None
+    roi = dist < thr
+    il = idx.long()
+    sigma = _span_cov2_torch(cp)[roi] + R @ _span_cov2_torch(ct)[il][roi] @ R.t()
+    d = (pred - tgt[il])[roi]
+    ref = ((d[:, None, :] @ torch.inverse(sigma) @ d[:, :, None]).reshape(-1).mean()
+           + 0.005 * (0.5 * torch.log(torch.det(sigma))).mean())
+    (ref * 1.7).backward()
+    want = [ref.detach().reshape(1), pred.grad, tgt.grad, cp.grad, ct.grad]
+    for a, b, name in zip(got, want, ["loss", "g_pred", "g_target", "g_cov_pred", "g_cov_target"]):
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-7, name
+
+
+def test_kabsch_fused_gather_and_weights(K):
+    """kabsch with the association gather + normal-cosine weights fused == explicit torch preparation."""
+    g = torch.Generator().manual_seed(9)
+    n, m = 4000, 3500
+    src = torch.randn(n, 3, generator=g).cuda() * 5
+    tgt = torch.randn(m, 3, generator=g).cuda() * 5
+    idx = torch.randint(0, m, (n,), generator=g, dtype=torch.int32).cuda()
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+    nrm[::7] = 0                                                   # zeroed normals, as the dataset makes them
+    dist = torch.rand(n, generator=g).cuda()
+    thr = torch.tensor([0.8]).cuda()
+    R1, t1 = K.kabsch(src, tgt, tgt_idx=idx, normal=nrm, dist=dist, dist_threshold=thr)
+    assoc = tgt[idx.long()].contiguous()
+    w = torch.nn.functional.cosine_similarity(nrm, assoc - src, dim=-1).abs()
+    R2, t2 = K.kabsch(src, assoc, weight=(w * w).contiguous(), dist=dist, dist_threshold=thr)
+    np.testing.assert_allclose(R1.cpu().numpy(), R2.cpu().numpy(), atol=1e-5)
+    np.testing.assert_allclose(t1.cpu().numpy(), t2.cpu().numpy(), atol=1e-4)
