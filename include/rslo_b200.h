@@ -117,10 +117,17 @@ int rslo_spconv_transpose_weight(const float* weight, int K, int Cin, int Cout, 
 int rslo_spconv_backward_data(const float* grad_out, const int32_t* nbr_t, int n_in_cap,
                               const int32_t* n_in_dev, int K, int Cin, int Cout, const float* weight_t,
                               float* grad_in, rslo_stream_t stream);
-/* dW[k] += in[nbr[o,k],:]^T (x) g[o,:]  (dW must be zeroed by the caller), dbias[c] += sum_o g. */
+/* dW[k] = sum_o in[nbr[o,k],:]^T (x) g[o,:], dbias[c] = sum_o g[o,c] (grad_bias may be NULL); both are
+ * zeroed inside. */
 int rslo_spconv_backward_weight(const float* in, const float* grad_out, const int32_t* nbr,
                                 int n_out_cap, const int32_t* n_out_dev, int K, int Cin, int Cout,
                                 float* grad_weight, float* grad_bias, rslo_stream_t stream);
+
+/* Activation backward fused with the bias gradient: grad_act = grad_out * (out > 0 ? 1 : slope) for
+ * act 1 (LeakyReLU, from the saved layer OUTPUT), grad_bias[c] = sum_o grad_act[o,c] (NULL to skip; zeroed
+ * inside).  act 0: bias gradient only (out / grad_act may be NULL). */
+int rslo_act_backward(const float* grad_out, const float* out, int n_cap, const int32_t* n_dev, int C, int act,
+                      float slope, float* grad_act, float* grad_bias, rslo_stream_t stream);
 
 /* Tensor-core variant for Cin, Cout in {32, 64} (csrc/spconv_tc.cu): tcgen05.mma kind::tf32 with a
  * 3xTF32 operand split (FP32-level accuracy), TMEM accumulator, weight tiles staged by bulk async copy.

@@ -39,6 +39,7 @@ SIGNATURES = {
     "rslo_spconv_transpose_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "rslo_spconv_backward_data": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rslo_spconv_backward_weight": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rslo_act_backward": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "rslo_spconv_tc_supported": (_i, [_i, _i, _i]),
     "rslo_spconv_tc_image_bytes": (_sz, [_i, _i, _i]),
     "rslo_spconv_tc_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -159,17 +159,37 @@ k_spconv_wgrad(const float* __restrict__ in, const float* __restrict__ g, const 
     }
 }
 
-// column sums: dbias[c] += sum_o g[o,c]
+// g_act[o,c] = g[o,c] * (out[o,c] > 0 ? 1 : slope)  (LeakyReLU backward from the saved OUTPUT; valid
+// because slope > 0 keeps the sign) fused with the bias gradient dbias[c] += sum_o g_act[o,c].
+// Thread (c, rl) walks rows rl, rl + rstep, ... so every global access is a coalesced row segment.
 __global__ void __launch_bounds__(256)
-k_colsum(const float* __restrict__ g, int n_cap, const int* n_dev, int C, float* __restrict__ out)
+k_act_bwd_colsum(const float* __restrict__ g, const float* __restrict__ out, int n_cap, const int* n_dev, int C,
+                 int act, float slope, float* __restrict__ g_act, float* __restrict__ dbias)
 {
     const int n = dev_count(n_dev, n_cap);
-    const int c = threadIdx.x % C;
-    const int rl = threadIdx.x / C, rstep = 256 / C;
-    if (rl >= rstep) return;
+    const int rstep = 256 / C;
+    const int c = threadIdx.x % C, rl = threadIdx.x / C;
     float s = 0.f;
-    for (int o = blockIdx.x * rstep + rl; o < n; o += gridDim.x * rstep) s += g[(size_t)o * C + c];
-    atomicAdd(out + c, s);
+    if (rl < rstep) {
+        for (int o = blockIdx.x * rstep + rl; o < n; o += gridDim.x * rstep) {
+            float v = g[(size_t)o * C + c];
+            if (act == 1) {
+                v = out[(size_t)o * C + c] > 0.f ? v : v * slope;
+                g_act[(size_t)o * C + c] = v;
+            }
+            s += v;
+        }
+    }
+    if (dbias) {
+        __shared__ float red[256];
+        red[threadIdx.x] = rl < rstep ? s : 0.f;
+        __syncthreads();
+        if (threadIdx.x < C) {
+            float t = 0.f;
+            for (int r = 0; r < rstep; ++r) t += red[r * C + threadIdx.x];
+            atomicAdd(dbias + threadIdx.x, t);
+        }
+    }
 }
 
 __global__ void k_dense(const float* __restrict__ feat, int C, const uint2* __restrict__ cells,
@@ -277,6 +297,8 @@ extern "C" int rslo_spconv_backward_weight(const float* in, const float* grad_ou
                                            rslo_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
+    RSLO_CHECK(cudaMemsetAsync(grad_weight, 0, (size_t)K * Cin * Cout * sizeof(float), st));
+    if (grad_bias) RSLO_CHECK(cudaMemsetAsync(grad_bias, 0, (size_t)Cout * sizeof(float), st));
     if (n_out_cap <= 0) return 0;
     dim3 grid(cdiv(n_out_cap, WG_ROWS), K);
     bool handled = false;
@@ -288,12 +310,31 @@ extern "C" int rslo_spconv_backward_weight(const float* in, const float* grad_ou
         return (int)cudaErrorInvalidValue;
     }
     if (grad_bias) {
-        int blocks = cdiv(n_out_cap, 256 / Cout * 64);
+        int blocks = cdiv(n_out_cap, 256 / Cout * 8);
         if (blocks > 148 * 4) blocks = 148 * 4;
         RSLO_COUNT();
-        k_colsum<<<blocks, 256, 0, st>>>(grad_out, n_out_cap, n_out_dev, Cout, grad_bias);
+        k_act_bwd_colsum<<<blocks, 256, 0, st>>>(grad_out, nullptr, n_out_cap, n_out_dev, Cout, 0, 0.f, nullptr,
+                                                 grad_bias);
     }
     RSLO_CHECK_LAUNCH("rslo_spconv_backward_weight");
+    return 0;
+}
+
+extern "C" int rslo_act_backward(const float* grad_out, const float* out, int n_cap, const int32_t* n_dev, int C,
+                                 int act, float slope, float* grad_act, float* grad_bias, rslo_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C < 1 || C > 256 || (act == 1 && (!out || !grad_act))) {
+        set_last_error("rslo_act_backward: bad argument", cudaErrorInvalidValue);
+        return (int)cudaErrorInvalidValue;
+    }
+    if (grad_bias) RSLO_CHECK(cudaMemsetAsync(grad_bias, 0, (size_t)C * sizeof(float), st));
+    if (n_cap <= 0) return 0;
+    int blocks = cdiv(n_cap, 256 / C * 8);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    RSLO_COUNT();
+    k_act_bwd_colsum<<<blocks, 256, 0, st>>>(grad_out, out, n_cap, n_dev, C, act, slope, grad_act, grad_bias);
+    RSLO_CHECK_LAUNCH("rslo_act_backward");
     return 0;
 }
 

@@ -321,13 +321,24 @@ def spconv_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=T
     nbr = _i32(nbr)
     K = nbr.shape[1]
     Cin, Cout = weight_shape[-2], weight_shape[-1]
-    gw = torch.zeros(tuple(weight_shape), dtype=torch.float32, device=g.device)
-    gb = torch.zeros(Cout, dtype=torch.float32, device=g.device) if need_bias else None
-    if n_out > 0:
-        check(lib.rslo_spconv_backward_weight(ptr(feat), ptr(g), ptr(nbr), n_out, None, K, Cin, Cout,
-                                              ptr(gw), ptr(gb), stream()), "rslo_spconv_backward_weight")
+    gw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=g.device)
+    gb = torch.empty(Cout, dtype=torch.float32, device=g.device) if need_bias else None
+    check(lib.rslo_spconv_backward_weight(ptr(feat), ptr(g), ptr(nbr), n_out, None, K, Cin, Cout,
+                                          ptr(gw), ptr(gb), stream()), "rslo_spconv_backward_weight")
     _count(2)
     return gw, gb
+
+
+def act_backward(grad_out, out, act, slope, need_bias=True):
+    """LeakyReLU backward from the saved output fused with the bias gradient -> (grad_act, grad_bias)."""
+    g = _f32(grad_out.contiguous())
+    n, Cc = g.shape
+    ga = torch.empty_like(g) if act else g
+    gb = torch.empty(Cc, dtype=torch.float32, device=g.device) if need_bias else None
+    check(lib.rslo_act_backward(ptr(g), ptr(out), n, None, Cc, int(act), float(slope), ptr(ga) if act else None,
+                                ptr(gb), stream()), "rslo_act_backward")
+    _count()
+    return ga, gb
 
 
 @_profiled("dense_from_sites", lambda out, feat, table: (feat.numel() * 4 + out.numel() * 4, 0))

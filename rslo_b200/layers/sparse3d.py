@@ -110,9 +110,9 @@ class _SpConvFn(torch.autograd.Function):
     def backward(ctx, g):
         feat, weight, out = ctx.saved_tensors
         e, inverse = ctx.entry, ctx.inverse
-        g = g.contiguous()
-        if ctx.act:
-            g = torch.where(out > 0, g, g * ctx.slope)
+        # LeakyReLU backward (from the saved output) and the bias gradient in one kernel
+        need_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        g, gb_fused = K.act_backward(g, out, ctx.act, ctx.slope, need_bias=need_gb)
         nbr = e.nbr_t if inverse else e.nbr
         nbr_t = e.nbr if inverse else e.nbr_t
         n_out = e.n_in if inverse else e.n_out
@@ -125,9 +125,9 @@ class _SpConvFn(torch.autograd.Function):
                 gi = K.spconv_tc_forward(g, nbr_t, n_in, img_t, Cout, Cin)
             else:
                 gi = K.spconv_backward_data(g, nbr_t, n_in, weight, e.mirror)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw, gb = K.spconv_backward_weight(feat, g, nbr, n_out, weight.shape, need_bias=ctx.has_bias)
-        return gi, gw, gb, None, None, None, None
+        if ctx.needs_input_grad[1]:
+            gw, _ = K.spconv_backward_weight(feat, g, nbr, n_out, weight.shape, need_bias=False)
+        return gi, gw, gb_fused, None, None, None, None
 
 
 def _triple(v):

@@ -50,7 +50,9 @@ def create_cycle_constraint_data(xs, cat_dim=1):
 def _detach_tree(x, to_cpu=False):
     if isinstance(x, torch.Tensor):
         x = x.detach()
-        return x.cpu() if to_cpu else x
+        # device results are cloned: the head's outputs live in CUDA-graph static buffers that the next
+        # call overwrites, while the reference hands out fresh tensors
+        return x.cpu() if to_cpu else x.clone()
     if isinstance(x, (list, tuple)):
         return [_detach_tree(v, to_cpu) for v in x]
     if isinstance(x, dict):
@@ -274,15 +276,15 @@ class UnVoxelOdomNetICP3(nn.Module):
             t_pred = t_pred[-1]
         if isinstance(r_pred, (list, tuple)):
             r_pred = r_pred[-1]
-        out = {"translation_preds": t_pred.detach(), "rotation_preds": r_pred.detach()}
+        out = {"translation_preds": _detach_tree(t_pred), "rotation_preds": _detach_tree(r_pred)}
         if self.testing:
-            out["middle_conf_preds"] = _detach_tree(list(preds_dict["middle_conf_preds"]))
-            out["voxel_features"] = _detach_tree(preds_dict["voxel_features"])
+            out["middle_conf_preds"] = [p.detach() for p in preds_dict["middle_conf_preds"]]
+            out["voxel_features"] = [p.detach() for p in preds_dict["voxel_features"]]
             out["normal_preds"] = []
-            out["tq_map_g"] = preds_dict["tq_map_g"].detach()
+            out["tq_map_g"] = _detach_tree(preds_dict["tq_map_g"])
             out["pyramid_motion"] = _detach_tree(preds_dict["pyramid_motion"])
-            out["t_conf"] = preds_dict["t_conf"].detach()
-            out["r_conf"] = preds_dict["r_conf"].detach()
+            out["t_conf"] = _detach_tree(preds_dict["t_conf"])
+            out["r_conf"] = _detach_tree(preds_dict["r_conf"])
             out["normal_gt"] = example.get("normal_gt", None)
         return out
 
@@ -303,7 +305,7 @@ class UnVoxelOdomNetICP3(nn.Module):
         self.end_timer("Create_loss forward")
         return {"loss": loss, "translation_loss": translation_loss.detach(), "rotation_loss": rotation_loss.detach(),
                 "pyramid_loss": pyramid_loss.detach(), "C_loss": C_loss.detach(),
-                "translation_preds": T_preds[0].detach(), "rotation_preds": R_preds[0].detach()}
+                "translation_preds": _detach_tree(T_preds[0]), "rotation_preds": _detach_tree(R_preds[0])}
 
     def create_loss(self, preds_dict, example, translation_loss, rotation_loss, pyramid_translation_loss=None,
                     pyramid_rotation_loss=None, pyramid_preds=None, consistency_loss=None):
@@ -369,12 +371,20 @@ class UnVoxelOdomNetICP3(nn.Module):
                     normal_target=transformed_normal1_gt.detach(), mask=None, icp_iter=icp_iter)
                 C_loss = C_loss + (1 - warm_weight) * weight * l
 
+        if (res_r is not None and len(pyramid_preds) > 0 and len(translation_preds) == 1
+                and pyramid_translation_loss is not None and pyramid_rotation_loss is not None):
+            # everything downstream of the ICP result has shapes fixed by the BEV grid: pseudo labels,
+            # target (t,q) maps, pose and pyramid losses run as one captured CUDA graph (fwd + bwd)
+            outs = self._loss_tail(translation_preds[0], rotation_preds[0], pyramid_preds, res_r, res_t,
+                                   identity_pose=step <= 1500)
+            n_py = len(pyramid_preds)
+            T_loss, R_loss = outs[0], outs[1]
+            pyramid_T_losses, pyramid_R_losses = list(outs[2:2 + n_py]), list(outs[2 + n_py:2 + 2 * n_py])
+            example["tq_maps"] = [outs[2 + 2 * n_py]]
+            return T_loss, R_loss, pyramid_T_losses, pyramid_R_losses, C_loss
+
         if res_r is not None and res_t is not None:
-            rotation_targets = res_r @ R_pred.detach()
-            rotation_targets = pose_utils.rotation_matrix_to_quaternion(rotation_targets)
-            rotation_targets = roll(rotation_targets, 1, dim=-1)
-            rotation_targets = rotation_targets * torch.sign(rotation_targets[:, 0:1])
-            translation_targets = (res_r @ T_pred[..., None].detach() + res_t[..., None]).squeeze(-1)
+            rotation_targets, translation_targets = self._pseudo_labels(res_r, res_t, R_pred, T_pred)
 
         if len(pyramid_preds) > 0:
             tq_map_targets = self.gen_tq_maps(
@@ -392,15 +402,87 @@ class UnVoxelOdomNetICP3(nn.Module):
             R_loss = R_loss + rotation_loss(p, rotation_targets)
         if pyramid_translation_loss is None or pyramid_rotation_loss is None:
             return T_loss, R_loss
+        pyramid_T_losses, pyramid_R_losses = self._pyramid_losses(pyramid_preds, pyramid_targets[0],
+                                                                  pyramid_translation_loss, pyramid_rotation_loss)
+        return T_loss, R_loss, pyramid_T_losses, pyramid_R_losses, C_loss
+
+    # ---- pieces of create_loss downstream of the ICP result (voxel_odom_net.py:727-795) ------------
+    @staticmethod
+    def _pseudo_labels(res_r, res_t, R_pred, T_pred):
+        rotation_targets = res_r @ R_pred.detach()
+        rotation_targets = pose_utils.rotation_matrix_to_quaternion(rotation_targets)
+        rotation_targets = roll(rotation_targets, 1, dim=-1)
+        rotation_targets = rotation_targets * torch.sign(rotation_targets[:, 0:1])
+        translation_targets = (res_r @ T_pred[..., None].detach() + res_t[..., None]).squeeze(-1)
+        return rotation_targets, translation_targets
+
+    @staticmethod
+    def _pyramid_losses(pyramid_preds, target_map, pyramid_translation_loss, pyramid_rotation_loss):
         pyramid_T_losses, pyramid_R_losses = [], []
         for i, _ in enumerate(pyramid_preds):
             T_pred_i, R_pred_i = pyramid_preds[i][0][:, :3], pyramid_preds[i][0][:, 3:]
             pred_mask = pyramid_preds[i][1]
-            T_target, R_target = pyramid_targets[0][:, :3], pyramid_targets[0][:, 3:]
+            T_target, R_target = target_map[:, :3], target_map[:, 3:]
             if T_target.shape != T_pred_i.shape:
                 T_target = F.interpolate(T_target, size=T_pred_i[0, 0].shape, mode="nearest")
             if R_target.shape != R_pred_i.shape:
                 R_target = F.interpolate(R_target, size=T_pred_i[0, 0].shape, mode="nearest")
             pyramid_T_losses.append(pyramid_translation_loss(T_pred_i, T_target, mask=pred_mask[:, :1]))
             pyramid_R_losses.append(pyramid_rotation_loss(R_pred_i, R_target, mask=pred_mask[:, -1:]))
-        return T_loss, R_loss, pyramid_T_losses, pyramid_R_losses, C_loss
+        return pyramid_T_losses, pyramid_R_losses
+
+    def _loss_tail_eager(self, T_pred, q_pred, pyramid_flat, res_r, res_t, identity_pose):
+        """(T_pred [B,3], q_pred [B,4], [pred_0, mask_0, pred_1, ...], res_r, res_t) ->
+        (T_loss, R_loss, pyT_0.., pyR_0.., tq_map_target)."""
+        pyramid_preds = [[pyramid_flat[2 * i], pyramid_flat[2 * i + 1]] for i in range(len(pyramid_flat) // 2)]
+        R_pred = pose_utils.quaternion_to_rotation_matrix(roll(q_pred, shift=-1, dim=-1))
+        T_used = T_pred
+        if identity_pose:                                   # step <= 1500 (voxel_odom_net.py:677-679)
+            R_pred = torch.eye(3, device=T_pred.device, dtype=T_pred.dtype).expand(R_pred.shape[0], 3, 3)
+            T_used = torch.zeros_like(T_pred)
+        rotation_targets, translation_targets = self._pseudo_labels(res_r, res_t, R_pred, T_used)
+        tq_map = self.gen_tq_maps(torch.cat([translation_targets, rotation_targets], dim=-1).reshape(-1, 7),
+                                  spatial_size=pyramid_preds[-1][0].shape[2:],
+                                  pc_range=self.odom_predictor.point_cloud_range,
+                                  cubic_tq_map=self.odom_predictor._cubic_pred_height > 0)[0]
+        T_loss = self._translation_loss(T_pred, translation_targets)
+        R_loss = self._rotation_loss(q_pred, rotation_targets)
+        pyT, pyR = self._pyramid_losses(pyramid_preds, tq_map, self._pyramid_translation_loss,
+                                        self._pyramid_rotation_loss)
+        return (T_loss, R_loss, *pyT, *pyR, tq_map)
+
+    def _loss_tail(self, T_pred, q_pred, pyramid_preds, res_r, res_t, identity_pose):
+        flat = []
+        for pred, mask in pyramid_preds:
+            flat += [pred, mask]
+        use_graph = odom_pred.UNRResNetOdomPredEncDecSVDTempMask.use_cuda_graph and T_pred.is_cuda
+        if not use_graph:
+            return self._loss_tail_eager(T_pred, q_pred, flat, res_r, res_t, identity_pose)
+        args = (T_pred, q_pred, *flat, res_r, res_t)
+        key = (identity_pose, self._translation_loss._loss_weight, self._rotation_loss._loss_weight,
+               tuple((tuple(a.shape), a.requires_grad) for a in args), T_pred.device.index)
+        cache = self.__dict__.setdefault("_graphed_tail", {})
+        g = cache.get(key)
+        if g is None:
+            mod = _LossTail(self, identity_pose)
+            sample = tuple(torch.rand_like(a).add_(0.5).requires_grad_(a.requires_grad) for a in args)
+            with torch.enable_grad():
+                g = torch.cuda.make_graphed_callables(mod, sample, allow_unused_input=True)
+            cache[key] = g
+        outs = g(*[a.contiguous() for a in args])
+        return tuple(o.clone() for o in outs)               # static graph buffers -> caller-owned tensors
+
+
+class _LossTail(nn.Module):
+    """Tensor-in / tensor-out view of the loss tail for CUDA-graph capture; shares the net's loss
+    modules (their learnable alphas are this module's parameters).  Never registered as a child of the
+    net, so the state_dict is unchanged."""
+
+    def __init__(self, net, identity_pose):
+        super().__init__()
+        self.__dict__["_net"] = net                          # plain reference, not a submodule
+        self.t_loss, self.r_loss = net._translation_loss, net._rotation_loss
+        self.identity_pose = identity_pose
+
+    def forward(self, T_pred, q_pred, *rest):
+        return self._net._loss_tail_eager(T_pred, q_pred, list(rest[:-2]), rest[-2], rest[-1], self.identity_pose)
