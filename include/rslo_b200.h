@@ -139,9 +139,11 @@ int rslo_spconv_tc_supported(int Cin, int Cout, int K);
 size_t rslo_spconv_tc_image_bytes(int K, int Cin, int Cout);
 int rslo_spconv_tc_prepare(const float* weight, int K, int Cin, int Cout, int transpose, int mirror,
                            float* image, rslo_stream_t stream);
+size_t rslo_spconv_tc_workspace_bytes(int n_out_cap, int ndim);
 int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n_out_cap, const int32_t* n_out_dev,
                            int K, int kdim, int ndim, const float* image, const float* bias, int act,
-                           float slope, float* out, rslo_stream_t stream);
+                           float slope, float* out, void* workspace, size_t workspace_bytes,
+                           rslo_stream_t stream);
 
 /* ---- a7: SparseConvTensor.dense() + view (middle.py:240-243) ------------------------------------
  * feat [n,C] at sites of a (D,H,W) level -> dense [C*D, H, W] f32 (zero where no site). */

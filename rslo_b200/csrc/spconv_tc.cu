@@ -12,22 +12,23 @@
 //
 // FP32 fidelity (the path's parity bound is 1e-4 relative, which plain TF32 misses): split-TF32.
 // Each operand is split as x ~= hi + lo with hi = RN_tf32(x) and lo = RN_tf32(x - hi) (x - hi is
-// exact in fp32), so the pair represents x to 2^-23 relative — fp32's own precision — and all four
-// products hi*hi + lo*hi + hi*lo + lo*lo are accumulated in the FP32 TMEM accumulator.  The splits
+// exact in fp32), so the pair represents x to 2^-23 relative — fp32's own precision — and the three
+// products lo*hi + hi*lo + hi*hi are accumulated (lo*lo is below 2^-24 relative).  The splits
 // are made while staging (A) / in the weight prep kernel (B), so the tensor core only ever sees
 // operands that are already TF32-exact (no dependence on how the hardware would round).
 //
-// Pipeline: 2 shared-memory stages; full[s] (producers + bulk-copy tx -> MMA), empty[s]
-// (tcgen05.commit -> producers), acc (last commit -> epilogue).
+// Pipeline (mbarriers): a step stages 32 input channels of one offset; full[2] (producers +
+// bulk-copy bytes -> MMA), empty[2] (tcgen05.commit -> producers), tfull[2] / tempty[2]
+// (double-buffered TMEM accumulator: MMA <-> drain warps).  Two 48 KB stages per CTA, two CTAs per SM.
+// Small levels are split over gridDim.y CTAs per tile (disjoint offsets) so all 148 SMs have work.
 #include "common.cuh"
 
 namespace rslo {
 namespace {
 
 constexpr int TC_ROWS = 128;
-constexpr int TC_STAGES = 2;
-constexpr int TC_PRODUCERS = 128;          // warps 0..3: gather, then epilogue
-constexpr int TC_THREADS = 160;            // + warp 4: TMEM owner and MMA issuer
+constexpr int TC_PRODUCERS = 128;          // warps 0..3: gather
+constexpr int TC_THREADS = 288;            // + warp 4: TMEM owner and MMA issuer; warps 5..8: drain + epilogue
 constexpr unsigned TC_SPIN_LIMIT = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,55 +141,73 @@ __global__ void k_tc_prep(const float* __restrict__ W, int K, int Cin, int Cout,
     if (!transpose) v = W[((size_t)k * Cin + kk) * Cout + n];
     else v = W[((size_t)(mirror ? K - 1 - k : k) * Cin + n) * Cout + kk];
     const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
-    char* base = (char*)img + (size_t)k * per * 8;
-    const uint32_t off = sw128_offset(n, kk, NDIM);
+    // image: per offset k, per 32-wide K block kb: {B_hi [NDIM x 32], B_lo [NDIM x 32]}, each SWIZZLE_128B K-major
+    const int kb = kk >> 5;
+    char* base = (char*)img + ((size_t)k * (KDIM / 32) + kb) * (size_t)(2 * NDIM * 128);
+    const uint32_t off = sw128_offset(n, kk & 31, NDIM);
     *(float*)(base + off) = hi;
-    *(float*)(base + (size_t)per * 4 + off) = lo;
+    *(float*)(base + (size_t)NDIM * 128 + off) = lo;
 }
+
+constexpr int TC_KS = 32;                  // K channels staged per pipeline step (one 128-byte swizzle row)
+constexpr int TC_STAGES = 2;
 
 template <int KDIM, int NDIM>
 struct TcSmem {
-    static constexpr int A_BYTES = TC_ROWS * KDIM * 4;             // one of {hi, lo}
-    static constexpr int B_BYTES = NDIM * KDIM * 4;                // one of {hi, lo}
+    static constexpr int A_BYTES = TC_ROWS * TC_KS * 4;            // one of {hi, lo}: 16 KB
+    static constexpr int B_BYTES = NDIM * TC_KS * 4;               // one of {hi, lo}
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int NBR_BYTES = TC_ROWS * 32 * 4;             // K <= 32
-    static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + NBR_BYTES + 256 + 1024;   // + barriers + alignment slack
+    static constexpr int NBR_BYTES = TC_ROWS * 27 * 4;             // K <= 27 (3x3x3)
+    static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + NBR_BYTES + 128 + 1024;   // + barriers + alignment slack
 };
 
+// Named barrier among the 128 drain threads only (barrier 0 is __syncthreads).
+__device__ __forceinline__ void drain_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// grid = (row tiles, split).  CTA (tile, sidx) handles every split-th active kernel offset of its tile;
+// with split > 1 each CTA parks its partial sums in `scratch` and the last one to finish adds them in
+// fixed order (deterministic), applies bias + activation and writes the rows.
 template <int KDIM, int NDIM>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap, const int* n_dev, int K,
             const float* __restrict__ bimg, const float* __restrict__ bias, int act, float slope,
-            float* __restrict__ out)
+            float* __restrict__ out, float* __restrict__ scratch, int* __restrict__ tile_counter)
 {
     using S = TcSmem<KDIM, NDIM>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     int* s_nbr = (int*)(smem + TC_STAGES * S::STAGE_BYTES);
     uint64_t* bars = (uint64_t*)(smem + TC_STAGES * S::STAGE_BYTES + S::NBR_BYTES);
-    uint64_t* full_bar = bars;                // [TC_STAGES]
-    uint64_t* empty_bar = bars + TC_STAGES;   // [TC_STAGES]
-    uint64_t* acc_bar = bars + 2 * TC_STAGES;
-    uint32_t* s_tmem = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+    uint64_t* full_bar = bars;                // [2] producers (+ weight-copy bytes) -> MMA
+    uint64_t* empty_bar = bars + 2;           // [2] MMA retired -> producers
+    uint64_t* tfull_bar = bars + 4;           // [2] accumulator buffer complete -> drain warps
+    uint64_t* tempty_bar = bars + 6;          // [2] drained -> MMA
+    uint32_t* s_tmem = (uint32_t*)(bars + 8);
     uint32_t* s_mask = s_tmem + 1;
+    int* s_last = (int*)(s_tmem + 2);
+    constexpr int NSUB = KDIM / TC_KS;        // pipeline steps per kernel offset
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = dev_count(n_dev, n_cap);
     const int row0 = blockIdx.x * TC_ROWS;
-    if (row0 >= n) return;                    // uniform per CTA
+    const int split = gridDim.y, sidx = blockIdx.y;
+    if (row0 >= n) return;                    // uniform per CTA (all splits of the tile agree)
+    constexpr int TCOLS = 2 * NDIM;           // two accumulator buffers (64 or 128 columns: powers of two)
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(full_bar + s, TC_PRODUCERS);
-            mbar_init(empty_bar + s, 1);
-        }
-        mbar_init(acc_bar, 1);
+        mbar_init(full_bar + 0, TC_PRODUCERS);
+        mbar_init(full_bar + 1, TC_PRODUCERS);
+        mbar_init(empty_bar + 0, 1);
+        mbar_init(empty_bar + 1, 1);
+        mbar_init(tfull_bar + 0, 1);
+        mbar_init(tfull_bar + 1, 1);
+        mbar_init(tempty_bar + 0, 128);
+        mbar_init(tempty_bar + 1, 128);
         *s_mask = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
-        constexpr int COLS = NDIM < 32 ? 32 : NDIM;
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(COLS)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TCOLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -208,58 +227,151 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned mask = *s_mask;
+    // this CTA's offsets: every split-th set bit of the tile's mask
+    unsigned mask = 0;
+    {
+        unsigned m = *s_mask;
+        for (int j = 0; m; ++j) {
+            const unsigned bit = m & (0u - m);
+            m ^= bit;
+            if (j % split == sidx) mask |= bit;
+        }
+    }
     const uint32_t tmem_base = *s_tmem;
 
     if (warp < 4) {
-        // ================= producers =================
-        constexpr int CHUNKS = KDIM / 4;                 // 16-byte chunks per row
-        constexpr int ROWS_PER_LD = 32 / CHUNKS;         // rows covered by one warp-wide load
+        // ================= producers: gather neighbour rows, split to TF32 hi/lo, swizzled store =================
+        constexpr int CHUNKS = TC_KS / 4;                // 16-byte chunks per staged row segment (128 B)
+        constexpr int ROWS_PER_LD = 32 / CHUNKS;         // 4 rows per warp-wide load
+        constexpr int NLD = 32 / ROWS_PER_LD;            // 8 loads per warp per step, all in flight together
         const int sub = lane / CHUNKS, c = lane % CHUNKS;
         unsigned m = mask;
         for (int it = 0; m; ++it) {
             const int k = __ffs(m) - 1;
             m &= m - 1;
-            const int s = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            mbar_wait(empty_bar + s, ph ^ 1);
-            uint8_t* stage = smem + s * S::STAGE_BYTES;
-            if (tid == 0) {
-                mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
-                bulk_copy_g2s(stage + 2 * S::A_BYTES, (const char*)bimg + (size_t)k * 2 * S::B_BYTES, 2 * S::B_BYTES,
-                              full_bar + s);
+#pragma unroll
+            for (int h = 0; h < NSUB; ++h) {
+                const int st = it * NSUB + h, s = st & 1;
+                float4 v[NLD];
+#pragma unroll
+                for (int j = 0; j < NLD; ++j) {          // loads do not touch the stage: issue before the wait
+                    const int r = warp * 32 + j * ROWS_PER_LD + sub;
+                    const int src = s_nbr[r * K + k];
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (src >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM + h * TC_KS) + c);
+                }
+                mbar_wait(empty_bar + s, ((st >> 1) & 1) ^ 1);
+                uint8_t* stage = smem + s * S::STAGE_BYTES;
+                if (tid == 0) {
+                    mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                    bulk_copy_g2s(stage + 2 * S::A_BYTES, (const char*)bimg + ((size_t)k * NSUB + h) * (2 * S::B_BYTES),
+                                  2 * S::B_BYTES, full_bar + s);
+                }
+                uint8_t* a_hi = stage;
+                uint8_t* a_lo = stage + S::A_BYTES;
+#pragma unroll
+                for (int j = 0; j < NLD; ++j) {
+                    const int r = warp * 32 + j * ROWS_PER_LD + sub;
+                    const float4 hh = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
+                    const float4 ll = make_float4(tf32_rn(v[j].x - hh.x), tf32_rn(v[j].y - hh.y), tf32_rn(v[j].z - hh.z),
+                                                  tf32_rn(v[j].w - hh.w));
+                    const uint32_t off = sw128_offset(r, c * 4, TC_ROWS);
+                    *reinterpret_cast<float4*>(a_hi + off) = hh;
+                    *reinterpret_cast<float4*>(a_lo + off) = ll;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+                mbar_arrive(full_bar + s);
             }
-            uint8_t* a_hi = stage;
-            uint8_t* a_lo = stage + S::A_BYTES;
-#pragma unroll 4
-            for (int j = 0; j < 32 / ROWS_PER_LD; ++j) {
-                const int r = warp * 32 + j * ROWS_PER_LD + sub;
-                const int src = s_nbr[r * K + k];
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src >= 0) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM) + c);
-                float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                float4 l = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
-                const uint32_t off = sw128_offset(r, c * 4, TC_ROWS);
-                *reinterpret_cast<float4*>(a_hi + off) = h;
-                *reinterpret_cast<float4*>(a_lo + off) = l;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-            mbar_arrive(full_bar + s);
         }
-        // ================= epilogue =================
-        const int o = row0 + warp * 32 + lane;
+    } else if (warp == 4) {
+        // ================= MMA issuer (one elected lane) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(NDIM);
+            unsigned m = mask;
+            for (int it = 0; m; ++it) {
+                m &= m - 1;
+                const int buf = it & 1;
+                mbar_wait(tempty_bar + buf, ((it >> 1) & 1) ^ 1);     // accumulator buffer drained
+                const uint32_t d = tmem_base + buf * NDIM;
+                uint32_t acc = 0;                                     // each offset starts a fresh accumulation
+#pragma unroll
+                for (int h = 0; h < NSUB; ++h) {
+                    const int st = it * NSUB + h, s = st & 1;
+                    mbar_wait(full_bar + s, (st >> 1) & 1);           // operands staged
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + S::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
+                    const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {            // lo*hi, hi*lo, hi*hi (lo*lo < 2^-24 relative)
+                        const uint32_t a = part == 0 ? a_lo : a_hi;
+                        const uint32_t b = part == 1 ? b_lo : b_hi;
+#pragma unroll
+                        for (int kk = 0; kk < TC_KS / 8; ++kk) {
+                            umma_tf32(d, umma_desc_k_sw128(a + kk * 32), umma_desc_k_sw128(b + kk * 32), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(empty_bar + s);        // stage reusable once these MMAs retire
+                }
+                umma_commit(tfull_bar + buf);          // this offset's partial product is complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= drain + epilogue warps (one output row per thread) =================
+        // The tensor core's accumulator adds are not round-to-nearest; only the 4*KDIM/8 MMAs of ONE
+        // offset accumulate in TMEM, the sum over offsets is carried here in FP32 registers (RN adds).
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;
+        const int o = row0 + r;
         float acc[NDIM];
-        if (mask) {
-            mbar_wait(acc_bar, 0);
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) acc[i] = 0.f;
+        unsigned m = mask;
+        for (int it = 0; m; ++it) {
+            m &= m - 1;
+            const int buf = it & 1;
+            mbar_wait(tfull_bar + buf, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NDIM;
 #pragma unroll
-            for (int cb = 0; cb < NDIM; cb += 16) tmem_ld16(taddr + cb, acc + cb);
-        } else {
+            for (int cb = 0; cb < NDIM; cb += 16) {
+                float v[16];
+                tmem_ld16(taddr + cb, v);
 #pragma unroll
-            for (int i = 0; i < NDIM; ++i) acc[i] = 0.f;
+                for (int i = 0; i < 16; ++i) acc[cb + i] += v[i];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty_bar + buf);
         }
-        if (o < n) {
+        bool finish = true;
+        if (split > 1) {
+            float4* mine = reinterpret_cast<float4*>(scratch + ((size_t)(blockIdx.x * split + sidx) * TC_ROWS + r) * NDIM);
+#pragma unroll
+            for (int i = 0; i < NDIM; i += 4) mine[i / 4] = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            __threadfence();
+            drain_sync();
+            if (warp == 5 && lane == 0) *s_last = atomicAdd(tile_counter + blockIdx.x, 1) == split - 1;
+            drain_sync();
+            finish = *s_last != 0;
+            if (finish) {
+                __threadfence();
+#pragma unroll
+                for (int i = 0; i < NDIM; ++i) acc[i] = 0.f;
+                for (int sp = 0; sp < split; ++sp) {           // fixed order: deterministic sum
+                    const float4* p = reinterpret_cast<const float4*>(
+                        scratch + ((size_t)(blockIdx.x * split + sp) * TC_ROWS + r) * NDIM);
+#pragma unroll
+                    for (int i = 0; i < NDIM; i += 4) {
+                        const float4 t = __ldcg(p + i / 4);
+                        acc[i] += t.x; acc[i + 1] += t.y; acc[i + 2] += t.z; acc[i + 3] += t.w;
+                    }
+                }
+            }
+        }
+        if (finish && o < n) {
             float4* dst = reinterpret_cast<float4*>(out + (size_t)o * NDIM);
 #pragma unroll
             for (int i = 0; i < NDIM; i += 4) {
@@ -277,53 +389,25 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 dst[i / 4] = v;
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else {
-        // ================= MMA issuer (one elected lane of warp 4) =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(NDIM);
-            unsigned m = mask;
-            uint32_t first = 1;
-            for (int it = 0; m; ++it) {
-                m &= m - 1;
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(full_bar + s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + S::A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
-                const uint32_t b_lo = b_hi + S::B_BYTES;
-#pragma unroll
-                for (int part = 0; part < 4; ++part) {                 // lo*lo, lo*hi, hi*lo, hi*hi
-                    const uint32_t a = (part & 2) ? a_hi : a_lo;
-                    const uint32_t b = (part & 1) ? b_hi : b_lo;
-#pragma unroll
-                    for (int kb = 0; kb < KDIM / 32; ++kb)
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t ad = umma_desc_k_sw128(a + kb * (TC_ROWS * 128) + kk * 32);
-                            const uint64_t bd = umma_desc_k_sw128(b + kb * (NDIM * 128) + kk * 32);
-                            umma_tf32(tmem_base, ad, bd, idesc, first ? 0u : 1u);
-                            first = 0;
-                        }
-                }
-                umma_commit(empty_bar + s);            // frees the stage when these MMAs retire
-            }
-            if (mask) umma_commit(acc_bar);            // accumulator complete -> epilogue
-        }
-        __syncwarp();
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 4) {
-        constexpr int COLS = NDIM < 32 ? 32 : NDIM;
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
+}
+
+static inline int tc_split_for(int n_cap)
+{
+    const int tiles = cdiv(n_cap, TC_ROWS);
+    int split = (2 * 148) / tiles;             // two CTAs are resident per SM: keep the whole grid in one wave
+    return split < 1 ? 1 : (split > 4 ? 4 : split);
 }
 
 template <int KDIM, int NDIM>
 int launch_tc(const float* in, const int* nbr, int n_cap, const int* n_dev, int K, const float* bimg,
-              const float* bias, int act, float slope, float* out, cudaStream_t st)
+              const float* bias, int act, float slope, float* out, void* workspace, size_t workspace_bytes,
+              cudaStream_t st)
 {
     using S = TcSmem<KDIM, NDIM>;
     static bool configured = false;
@@ -331,9 +415,23 @@ int launch_tc(const float* in, const int* nbr, int n_cap, const int* n_dev, int 
         RSLO_CHECK(cudaFuncSetAttribute(k_spconv_tc<KDIM, NDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         configured = true;
     }
+    const int tiles = cdiv(n_cap, TC_ROWS);
+    const int split = tc_split_for(n_cap);
+    float* scratch = nullptr;
+    int* counter = nullptr;
+    if (split > 1) {
+        Workspace ws(workspace, workspace_bytes);
+        counter = ws.take<int>(tiles);
+        scratch = ws.take<float>((size_t)tiles * split * TC_ROWS * NDIM);
+        if (!scratch) {
+            set_last_error("rslo_spconv_tc_forward: workspace too small", cudaErrorMemoryAllocation);
+            return (int)cudaErrorMemoryAllocation;
+        }
+        RSLO_CHECK(cudaMemsetAsync(counter, 0, (size_t)tiles * sizeof(int), st));
+    }
     RSLO_COUNT();
-    k_spconv_tc<KDIM, NDIM><<<cdiv(n_cap, TC_ROWS), TC_THREADS, S::TOTAL, st>>>(in, nbr, n_cap, n_dev, K, bimg, bias, act,
-                                                                              slope, out);
+    k_spconv_tc<KDIM, NDIM><<<dim3(tiles, split), TC_THREADS, S::TOTAL, st>>>(in, nbr, n_cap, n_dev, K, bimg, bias, act,
+                                                                             slope, out, scratch, counter);
     RSLO_CHECK_LAUNCH("rslo_spconv_tc");
     return 0;
 }
@@ -345,7 +443,7 @@ using namespace rslo;
 
 extern "C" int rslo_spconv_tc_supported(int Cin, int Cout, int K)
 {
-    return (Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64) && K >= 1 && K <= 32;
+    return (Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64) && K >= 1 && K <= 27;
 }
 
 extern "C" size_t rslo_spconv_tc_image_bytes(int K, int Cin, int Cout) { return (size_t)K * Cin * Cout * 8; }
@@ -364,20 +462,34 @@ extern "C" int rslo_spconv_tc_prepare(const float* weight, int K, int Cin, int C
     return 0;
 }
 
+extern "C" size_t rslo_spconv_tc_workspace_bytes(int n_out_cap, int ndim)
+{
+    const int tiles = cdiv(n_out_cap > 0 ? n_out_cap : 1, TC_ROWS);
+    const int split = tc_split_for(n_out_cap > 0 ? n_out_cap : 1);
+    if (split <= 1) return 256;
+    return ws_round((size_t)tiles * sizeof(int)) + ws_round((size_t)tiles * split * TC_ROWS * ndim * sizeof(float)) + 256;
+}
+
 extern "C" int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n_out_cap, const int32_t* n_out_dev,
                                       int K, int kdim, int ndim, const float* image, const float* bias, int act,
-                                      float slope, float* out, rslo_stream_t stream)
+                                      float slope, float* out, void* workspace, size_t workspace_bytes,
+                                      rslo_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_out_cap <= 0) return 0;
-    if (K < 1 || K > 32) {
-        set_last_error("rslo_spconv_tc_forward: K must be in 1..32", cudaErrorInvalidValue);
+    if (K < 1 || K > 27) {
+        set_last_error("rslo_spconv_tc_forward: K must be in 1..27", cudaErrorInvalidValue);
         return (int)cudaErrorInvalidValue;
     }
-    if (kdim == 64 && ndim == 64) return launch_tc<64, 64>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
-    if (kdim == 64 && ndim == 32) return launch_tc<64, 32>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
-    if (kdim == 32 && ndim == 64) return launch_tc<32, 64>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
-    if (kdim == 32 && ndim == 32) return launch_tc<32, 32>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, st);
+#define RSLO_TC_CASE(KD, ND)                                                                                      \
+    if (kdim == KD && ndim == ND)                                                                                 \
+        return launch_tc<KD, ND>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, workspace,       \
+                                 workspace_bytes, st);
+    RSLO_TC_CASE(64, 64)
+    RSLO_TC_CASE(64, 32)
+    RSLO_TC_CASE(32, 64)
+    RSLO_TC_CASE(32, 32)
+#undef RSLO_TC_CASE
     set_last_error("rslo_spconv_tc_forward: unsupported (kdim, ndim)", cudaErrorInvalidValue);
     return (int)cudaErrorInvalidValue;
 }

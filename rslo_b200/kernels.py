@@ -290,8 +290,10 @@ def spconv_tc_forward(feat, nbr, n_out, image, kdim, ndim, bias=None, act=0, slo
     out = torch.empty((n_out, ndim), dtype=torch.float32, device=feat.device)
     if n_out == 0:
         return out
+    ws = workspace(lib.rslo_spconv_tc_workspace_bytes(n_out, ndim), "spconv_tc")
     check(lib.rslo_spconv_tc_forward(ptr(feat), ptr(nbr), n_out, ptr(n_out_dev), nbr.shape[1], kdim, ndim, ptr(image),
-                                     ptr(bias), act, float(slope), ptr(out), stream()), "rslo_spconv_tc_forward")
+                                     ptr(bias), act, float(slope), ptr(out), ptr(ws), ws.numel(), stream()),
+          "rslo_spconv_tc_forward")
     _count()
     return out
 

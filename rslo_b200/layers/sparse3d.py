@@ -67,9 +67,10 @@ class SparseConvTensor:
         return out.view(1, self.features.shape[1], D, H, W)
 
 
-# Layers with Cin, Cout in {32, 64} can run on the tcgen05 tensor-core kernel (csrc/spconv_tc.cu,
-# split-TF32); the narrow layers (7/16 channels) stay on the FP32 FFMA kernel.
-USE_TC = os.environ.get("RSLO_SPCONV_TC", "0") == "1"
+# Layers with Cin, Cout in {32, 64} run on the tcgen05 tensor-core kernel (csrc/spconv_tc.cu, split-TF32,
+# FP32-level accuracy); the narrow layers (7/16 channels) stay on the FP32 FFMA kernel.
+# RSLO_SPCONV_TC=0 forces the FFMA kernel everywhere.
+USE_TC = os.environ.get("RSLO_SPCONV_TC", "1") != "0"
 
 
 class _DenseFn(torch.autograd.Function):

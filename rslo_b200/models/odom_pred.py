@@ -30,6 +30,8 @@ REGISTERED_ODOM_PRED_CLASSES = {}
 # The 2-D convolutions run in true FP32: cuDNN's default TF32 path gives ~1e-3 pose error, outside the
 # 1e-4 relative parity bound of the path (measured on B200, tests/test_gpu_pair.py).
 HEAD_ALLOW_TF32 = False
+# cuDNN autotuning of the head's FP32 convolutions (shapes are static; tuned once before graph capture).
+HEAD_CUDNN_BENCHMARK = os.environ.get("RSLO_CUDNN_BENCHMARK", "1") != "0"
 
 
 def register_odom_pred(cls, name=None):
@@ -221,7 +223,7 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
     def forward(self, xs, tq_map_gt=None, local_spatial_features=None, **kwargs):
         if not isinstance(xs, list):
             xs = [xs]
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=HEAD_ALLOW_TF32):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=HEAD_ALLOW_TF32, benchmark=HEAD_CUDNN_BENCHMARK):
             if self.use_cuda_graph and xs[0].is_cuda and self.dense_predict and self.pred_pyramid_motion:
                 return self._forward_graphed(xs)
             return self._forward(xs, tq_map_gt, local_spatial_features, **kwargs)

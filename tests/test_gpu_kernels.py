@@ -225,11 +225,14 @@ def test_nn_bit_exact(K, scan_pair, n, m, kind):
         assert np.array_equal(r[0].cpu().numpy(), d_ref)
 
 
-@pytest.mark.parametrize("cin,cout,K_", [(64, 64, 27), (32, 32, 27), (32, 64, 27), (64, 32, 27), (64, 64, 3)])
-def test_spconv_tensor_core_forward(K, cin, cout, K_):
-    """tcgen05 3xTF32 implicit-GEMM kernel vs the oracle's gather-conv: FP32-level agreement."""
+@pytest.mark.parametrize("cin,cout,K_,n_out", [(64, 64, 27, 2577), (32, 32, 27, 2577), (32, 64, 27, 2577),
+                                               (64, 32, 27, 2577), (64, 64, 3, 2577), (64, 64, 27, 19594),
+                                               (32, 32, 27, 40001)])
+def test_spconv_tensor_core_forward(K, cin, cout, K_, n_out):
+    """tcgen05 split-TF32 implicit-GEMM kernel vs the oracle's gather-conv: FP32-level agreement.
+    Row counts cover the offset-split paths (4-way, 2-way) and the unsplit one."""
     g = torch.Generator().manual_seed(cin * 100 + cout + K_)
-    n_in, n_out = 3000, 2500 + 77            # not a multiple of the 128-row tile
+    n_in = 3000                              # n_out is not a multiple of the 128-row tile
     nbr = torch.randint(0, n_in, (n_out, K_), generator=g, dtype=torch.int32)
     nbr[torch.rand((n_out, K_), generator=g) < 0.6] = -1
     nbr[128:256] = -1                        # a whole tile without any neighbour -> bias only
@@ -241,8 +244,9 @@ def test_spconv_tensor_core_forward(K, cin, cout, K_):
     img = K.spconv_tc_prepare(w.cuda())
     out = K.spconv_tc_forward(feat.cuda(), nbr.cuda(), n_out, img, cin, cout, b.cuda(), act=1, slope=0.01)
     torch.cuda.synchronize()
-    # 3xTF32: ~1e-5 relative (tensor-core accumulation is not full IEEE fp32); the path bound is 1e-4
-    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=5e-5, atol=1e-4)
+    err = (out.cpu() - ref).abs().max().item()
+    print(f"tc max abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-5)
     # data gradient through the transposed image == FFMA data-gradient kernel == autograd
     go = torch.randn((n_out, cout), generator=g)
     n_t = 2000
@@ -252,7 +256,7 @@ def test_spconv_tensor_core_forward(K, cin, cout, K_):
         img_t = K.spconv_tc_prepare(w.cuda(), transpose=True, mirror=mirror)
         gi = K.spconv_tc_forward(go.cuda(), nbr_t.cuda(), n_t, img_t, cout, cin)
         gi_ref = K.spconv_backward_data(go.cuda(), nbr_t.cuda(), n_t, w.cuda(), mirror)
-        np.testing.assert_allclose(gi.cpu().numpy(), gi_ref.cpu().numpy(), rtol=5e-5, atol=1e-4)
+        np.testing.assert_allclose(gi.cpu().numpy(), gi_ref.cpu().numpy(), rtol=1e-5, atol=2e-5)
 
 
 def _span_cov2_torch(p):
