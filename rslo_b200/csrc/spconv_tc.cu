@@ -11,15 +11,16 @@
 // bias + LeakyReLU and writes the rows.
 //
 // FP32 fidelity (the path's parity bound is 1e-4 relative, which plain TF32 misses): split-TF32.
-// Each operand is split as x ~= hi + lo with hi = RN_tf32(x) and lo = RN_tf32(x - hi) (x - hi is
-// exact in fp32), so the pair represents x to 2^-23 relative — fp32's own precision — and the three
-// products lo*hi + hi*lo + hi*hi are accumulated (lo*lo is below 2^-24 relative).  The splits
+// Each operand is split as x = hi + lo with hi = RN_tf32(x) and lo = x - hi (exact in fp32, |lo| <=
+// 2^-12 |x|; the tensor core keeps lo's top 11 bits, so the pair represents x to ~2^-22 relative), and
+// the three products lo*hi + hi*lo + hi*hi are accumulated (lo*lo is below 2^-24 relative).  The splits
 // are made while staging (A) / in the weight prep kernel (B), so the tensor core only ever sees
 // operands that are already TF32-exact (no dependence on how the hardware would round).
 //
 // Pipeline (mbarriers): a step stages 32 input channels of one offset; full[2] (producers +
 // bulk-copy bytes -> MMA), empty[2] (tcgen05.commit -> producers), tfull[2] / tempty[2]
-// (double-buffered TMEM accumulator: MMA <-> drain warps).  Two 48 KB stages per CTA, two CTAs per SM.
+// (double-buffered TMEM accumulator: MMA <-> drain warps).  Two 48 KB stages per CTA, two CTAs per SM
+// (measured faster than four stages with one CTA per SM: 51 vs 58 us on the 19.6k-row 64->64 layer).
 // Small levels are split over gridDim.y CTAs per tile (disjoint offsets) so all 148 SMs have work.
 #include "common.cuh"
 
@@ -123,6 +124,11 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, int 
            (uint32_t)((c16 ^ r8) << 4) + (uint32_t)(col & 3) * 4u;
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // round-to-nearest (ties away) onto TF32's 10-bit mantissa; the carry may ripple into the exponent
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
@@ -158,7 +164,7 @@ struct TcSmem {
     static constexpr int B_BYTES = NDIM * TC_KS * 4;               // one of {hi, lo}
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int NBR_BYTES = TC_ROWS * 27 * 4;             // K <= 27 (3x3x3)
-    static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + NBR_BYTES + 128 + 1024;   // + barriers + alignment slack
+    static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + NBR_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
 
 // Named barrier among the 128 drain threads only (barrier 0 is __syncthreads).
@@ -178,13 +184,14 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     int* s_nbr = (int*)(smem + TC_STAGES * S::STAGE_BYTES);
     uint64_t* bars = (uint64_t*)(smem + TC_STAGES * S::STAGE_BYTES + S::NBR_BYTES);
-    uint64_t* full_bar = bars;                // [2] producers (+ weight-copy bytes) -> MMA
-    uint64_t* empty_bar = bars + 2;           // [2] MMA retired -> producers
-    uint64_t* tfull_bar = bars + 4;           // [2] accumulator buffer complete -> drain warps
-    uint64_t* tempty_bar = bars + 6;          // [2] drained -> MMA
-    uint32_t* s_tmem = (uint32_t*)(bars + 8);
+    uint64_t* full_bar = bars;                          // [TC_STAGES] producers (+ weight-copy bytes) -> MMA
+    uint64_t* empty_bar = bars + TC_STAGES;             // [TC_STAGES] MMA retired -> producers
+    uint64_t* tfull_bar = bars + 2 * TC_STAGES;         // [2] accumulator buffer complete -> drain warps
+    uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2;    // [2] drained -> MMA
+    uint32_t* s_tmem = (uint32_t*)(bars + 2 * TC_STAGES + 4);
     uint32_t* s_mask = s_tmem + 1;
     int* s_last = (int*)(s_tmem + 2);
+    int* s_klist = (int*)(s_tmem + 3);        // [27]
     constexpr int NSUB = KDIM / TC_KS;        // pipeline steps per kernel offset
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -195,10 +202,10 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     constexpr int TCOLS = 2 * NDIM;           // two accumulator buffers (64 or 128 columns: powers of two)
 
     if (tid == 0) {
-        mbar_init(full_bar + 0, TC_PRODUCERS);
-        mbar_init(full_bar + 1, TC_PRODUCERS);
-        mbar_init(empty_bar + 0, 1);
-        mbar_init(empty_bar + 1, 1);
+        for (int i = 0; i < TC_STAGES; ++i) {
+            mbar_init(full_bar + i, TC_PRODUCERS);
+            mbar_init(empty_bar + i, 1);
+        }
         mbar_init(tfull_bar + 0, 1);
         mbar_init(tfull_bar + 1, 1);
         mbar_init(tempty_bar + 0, 128);
@@ -238,6 +245,14 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         }
     }
     const uint32_t tmem_base = *s_tmem;
+    if (tid == 0) {                           // this CTA's offsets in order, for indexed access by step
+        unsigned m = mask;
+        for (int j = 0; m; ++j) {
+            s_klist[j] = __ffs(m) - 1;
+            m &= m - 1;
+        }
+    }
+    __syncthreads();
 
     if (warp < 4) {
         // ================= producers: gather neighbour rows, split to TF32 hi/lo, swizzled store =================
@@ -245,43 +260,54 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         constexpr int ROWS_PER_LD = 32 / CHUNKS;         // 4 rows per warp-wide load
         constexpr int NLD = 32 / ROWS_PER_LD;            // 8 loads per warp per step, all in flight together
         const int sub = lane / CHUNKS, c = lane % CHUNKS;
-        unsigned m = mask;
-        for (int it = 0; m; ++it) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
+        const uint32_t smem_base = smem_u32(smem);
+        // per-thread swizzled store offsets of its NLD row segments (same for every step)
+        uint32_t soff[NLD];
 #pragma unroll
-            for (int h = 0; h < NSUB; ++h) {
-                const int st = it * NSUB + h, s = st & 1;
-                float4 v[NLD];
+        for (int j = 0; j < NLD; ++j) soff[j] = sw128_offset(warp * 32 + j * ROWS_PER_LD + sub, c * 4, TC_ROWS);
+        int nsteps = __popc(mask) * NSUB;
+
+        // gather of step st: NLD independent 16-byte loads (zeros for rows without this neighbour)
+        auto gather = [&](int k, int h, float4(&v)[NLD]) {
 #pragma unroll
-                for (int j = 0; j < NLD; ++j) {          // loads do not touch the stage: issue before the wait
-                    const int r = warp * 32 + j * ROWS_PER_LD + sub;
-                    const int src = s_nbr[r * K + k];
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (src >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM + h * TC_KS) + c);
-                }
-                mbar_wait(empty_bar + s, ((st >> 1) & 1) ^ 1);
-                uint8_t* stage = smem + s * S::STAGE_BYTES;
-                if (tid == 0) {
-                    mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
-                    bulk_copy_g2s(stage + 2 * S::A_BYTES, (const char*)bimg + ((size_t)k * NSUB + h) * (2 * S::B_BYTES),
-                                  2 * S::B_BYTES, full_bar + s);
-                }
-                uint8_t* a_hi = stage;
-                uint8_t* a_lo = stage + S::A_BYTES;
-#pragma unroll
-                for (int j = 0; j < NLD; ++j) {
-                    const int r = warp * 32 + j * ROWS_PER_LD + sub;
-                    const float4 hh = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
-                    const float4 ll = make_float4(tf32_rn(v[j].x - hh.x), tf32_rn(v[j].y - hh.y), tf32_rn(v[j].z - hh.z),
-                                                  tf32_rn(v[j].w - hh.w));
-                    const uint32_t off = sw128_offset(r, c * 4, TC_ROWS);
-                    *reinterpret_cast<float4*>(a_hi + off) = hh;
-                    *reinterpret_cast<float4*>(a_lo + off) = ll;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-                mbar_arrive(full_bar + s);
+            for (int j = 0; j < NLD; ++j) {
+                const int r = warp * 32 + j * ROWS_PER_LD + sub;
+                const int src = s_nbr[r * K + k];
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM + h * TC_KS) + c);
             }
+        };
+        // split to TF32 {hi, lo} and store into stage s in the UMMA layout; then publish the stage
+        auto publish = [&](int st, int k, int h, const float4(&v)[NLD]) {
+            const int s = st % TC_STAGES;
+            mbar_wait(empty_bar + s, ((st / TC_STAGES) & 1) ^ 1);
+            const uint32_t stage = smem_base + s * S::STAGE_BYTES;
+            if (tid == 0) {
+                mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
+                bulk_copy_g2s(smem + s * S::STAGE_BYTES + 2 * S::A_BYTES,
+                              (const char*)bimg + ((size_t)k * NSUB + h) * (2 * S::B_BYTES), 2 * S::B_BYTES, full_bar + s);
+            }
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) {
+                const float4 hh = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
+                const float4 ll = make_float4(v[j].x - hh.x, v[j].y - hh.y, v[j].z - hh.z, v[j].w - hh.w);
+                sts128(stage + soff[j], hh);
+                sts128(stage + S::A_BYTES + soff[j], ll);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+            mbar_arrive(full_bar + s);
+        };
+        // software pipeline: the loads of step st+1 are in flight while step st is split and stored
+        // (two rotating register buffers; measured: the producers, not the MMAs, pace this kernel)
+        auto kof = [&](int st) { return s_klist[st / NSUB]; };
+        float4 va[NLD], vb[NLD];
+        if (nsteps > 0) gather(kof(0), 0, va);
+        for (int st = 0; st < nsteps; st += 2) {
+            if (st + 1 < nsteps) gather(kof(st + 1), (st + 1) % NSUB, vb);
+            publish(st, kof(st), st % NSUB, va);
+            if (st + 1 >= nsteps) break;
+            if (st + 2 < nsteps) gather(kof(st + 2), (st + 2) % NSUB, va);
+            publish(st + 1, kof(st + 1), (st + 1) % NSUB, vb);
         }
     } else if (warp == 4) {
         // ================= MMA issuer (one elected lane) =================
@@ -296,8 +322,8 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 uint32_t acc = 0;                                     // each offset starts a fresh accumulation
 #pragma unroll
                 for (int h = 0; h < NSUB; ++h) {
-                    const int st = it * NSUB + h, s = st & 1;
-                    mbar_wait(full_bar + s, (st >> 1) & 1);           // operands staged
+                    const int st = it * NSUB + h, s = st % TC_STAGES;
+                    mbar_wait(full_bar + s, (st / TC_STAGES) & 1);    // operands staged
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
                     const uint32_t a_lo = a_hi + S::A_BYTES;
@@ -397,10 +423,12 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     }
 }
 
+// Offsets of a tile are split over `split` CTAs when the level is too small to fill the GPU (two CTAs
+// are resident per SM): the largest split in 1..4 that keeps the whole grid in one wave.
 static inline int tc_split_for(int n_cap)
 {
     const int tiles = cdiv(n_cap, TC_ROWS);
-    int split = (2 * 148) / tiles;             // two CTAs are resident per SM: keep the whole grid in one wave
+    const int split = (2 * 148) / tiles;
     return split < 1 ? 1 : (split > 4 ? 4 : split);
 }
 
