@@ -96,6 +96,10 @@ int rslo_strided_table(const int32_t* coors, int coor_stride, int n_cap, const i
                        int32_t* n_out_dev, int32_t* nbr, int32_t* nbr_inv, void* workspace,
                        size_t workspace_bytes, rslo_stream_t stream);
 
+/* Several frames share one pass through the encoder: their tables are appended row-wise, row indices of
+ * frame f shifted by the number of rows before it.  dst[i] = src[i] >= 0 ? src[i] + add : -1. */
+int rslo_table_concat(const int32_t* src, long long count, int add, int32_t* dst, rslo_stream_t stream);
+
 /* ---- a6: sparse convolution ---------------------------------------------------------------------
  * out[o,:] = act( scale * (bias + sum_k in[nbr[o,k],:] @ W[k]) + shift )
  * Replaces Fsp.indice_conv / indice_inverse_conv + the LeakyReLU (and eval-mode BatchNorm1d of the

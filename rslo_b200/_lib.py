@@ -35,6 +35,7 @@ SIGNATURES = {
     "rslo_strided_workspace_bytes": (_sz, [_i, _i, _i]),
     "rslo_strided_table": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                 _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rslo_table_concat": (_i, [_vp, C.c_longlong, _i, _vp, _vp]),
     "rslo_spconv_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "rslo_spconv_transpose_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "rslo_spconv_backward_data": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),

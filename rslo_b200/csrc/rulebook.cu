@@ -124,6 +124,17 @@ __global__ void k_strided_table(const int* __restrict__ coors, int stride, int n
     nbr_inv[t] = o;
 }
 
+// dst[i] = src[i] >= 0 ? src[i] + add : -1 : appends one frame's table to a multi-frame table whose
+// rows of that frame start `add` rows further down
+__global__ void k_table_concat(const int* __restrict__ src, long long count, int add, int* __restrict__ dst)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t < count; t += (long long)gridDim.x * blockDim.x) {
+        const int v = src[t];
+        dst[t] = v >= 0 ? v + add : -1;
+    }
+}
+
 // n[1] = raw number of output sites, n[0] = min(raw, cap): callers detect overflow from n[1] > cap
 __global__ void k_clamp_count(int* n, int cap)
 {
@@ -225,5 +236,16 @@ extern "C" int rslo_strided_table(const int32_t* coors, int coor_stride, int n_c
     RSLO_COUNT();
     k_strided_table<<<G, 256, 0, st>>>(coors, coor_stride, n_cap, n_dev, g, out_cells, out_cap, nbr, nbr_inv);
     RSLO_CHECK_LAUNCH("rslo_strided_table");
+    return 0;
+}
+
+extern "C" int rslo_table_concat(const int32_t* src, long long count, int add, int32_t* dst, rslo_stream_t stream)
+{
+    if (count <= 0) return 0;
+    int blocks = cdiv(count, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    RSLO_COUNT();
+    k_table_concat<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, count, add, dst);
+    RSLO_CHECK_LAUNCH("rslo_table_concat");
     return 0;
 }

@@ -186,6 +186,21 @@ def strided_table(coors, n, shape, ksize, stride, pad, n_dev=None, out_cap=None)
     return SiteTable((oD, oH, oW), cells, None), out_coors, n_out_dev, nbr, nbr_inv
 
 
+def table_concat(tables, rows, adds):
+    """Row-wise concatenation of per-frame tables [rows_f, K] with row indices shifted by adds[f]."""
+    Kk = tables[0].shape[1]
+    total = int(sum(rows))
+    out = torch.empty((max(total, 1), Kk), dtype=torch.int32, device=tables[0].device)
+    r0 = 0
+    for t, r, a in zip(tables, rows, adds):
+        if r > 0:
+            check(lib.rslo_table_concat(ptr(_i32(t)), int(r) * Kk, int(a), ptr(out[r0:r0 + r]), stream()),
+                  "rslo_table_concat")
+            _count()
+        r0 += r
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # voxeliser
 # ------------------------------------------------------------------------------------------------

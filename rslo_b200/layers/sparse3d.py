@@ -28,6 +28,7 @@ class IndexEntry:
         self.out_shape = out_shape
         self.out_table = out_table      # kernels.SiteTable of the output level
         self.mirror = mirror            # transposed filter bank uses mirrored offsets (subm)
+        self.seg_in = self.seg_out = None   # rows per frame on each side when several frames share a pass
 
 
 class SparseConvTensor:
@@ -41,6 +42,8 @@ class SparseConvTensor:
         self.indice_dict = {}
         self.table = table              # kernels.SiteTable or None (built on demand)
         self.n = int(features.shape[0])
+        self.seg = None                 # rows per frame when several frames share this tensor
+        self.frames = None              # per-frame (row offset, rows, SiteTable) of this level, for dense()
 
     def _site_table(self):
         if self.table is None:
@@ -50,14 +53,25 @@ class SparseConvTensor:
     def find_indice_pair(self, key):
         return self.indice_dict.get(key) if key is not None else None
 
-    def shadow(self, features, indices=None, spatial_shape=None, table=None, n=None):
-        t = SparseConvTensor(features, self.indices if indices is None else indices,
+    def shadow(self, features, indices=None, spatial_shape=None, table=None, n=None, seg=None, frames=None,
+               new_sites=False):
+        keep = indices is None and not new_sites
+        t = SparseConvTensor(features, self.indices if keep else indices,
                              self.spatial_shape if spatial_shape is None else spatial_shape,
-                             self.batch_size, self.table if indices is None else table)
+                             self.batch_size, self.table if keep else table)
         t.indice_dict = self.indice_dict
         if n is not None:
             t.n = n
+        t.seg = self.seg if keep else seg
+        t.frames = self.frames if keep else frames
         return t
+
+    def dense_frames(self):
+        """One dense [1, C*D, H, W] map per frame of a multi-frame tensor (middle.py:240-243 per frame)."""
+        assert self.frames is not None
+        D, H, W = self.spatial_shape
+        outs = _DenseFramesFn.apply(self.features, self)
+        return [o.view(1, self.features.shape[1] * D, H, W) for o in outs]
 
     def dense(self):
         """[B, C, D, H, W] (`SparseConvTensor.dense()`, used at middle.py:240)."""
@@ -84,6 +98,27 @@ class _DenseFn(torch.autograd.Function):
     def backward(ctx, g):
         st = ctx.st
         return K.dense_backward(g, st.indices, st.n, st.spatial_shape, ctx.C), None, None
+
+
+class _DenseFramesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, st):
+        ctx.st = st
+        feat = feat.contiguous()
+        outs = []
+        for off, rows, table, _ in st.frames:
+            outs.append(K.dense_from_sites(feat[off:off + rows], table))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        st = ctx.st
+        C_ = gs[0].shape[0] // st.spatial_shape[0]
+        grad = torch.empty((st.n, C_), dtype=gs[0].dtype, device=gs[0].device)
+        for g, (off, rows, table, coors) in zip(gs, st.frames):
+            if rows > 0:
+                grad[off:off + rows] = K.dense_backward(g, coors, rows, st.spatial_shape, C_)
+        return grad, None
 
 
 class _SpConvFn(torch.autograd.Function):
@@ -181,10 +216,12 @@ class SparseConvolution(nn.Module):
         out = _SpConvFn.apply(x.features, w, self.bias, e, self.inverse, self.fused_act, self.fused_slope)
         if self.inverse:
             # lands on the INPUT site set of the keyed conv
-            return x.shadow(out, e.in_indices, e.in_shape, e.in_table, e.n_in)
+            return x.shadow(out, e.in_indices, e.in_shape, e.in_table, e.n_in, seg=e.seg_in,
+                            frames=getattr(e, "in_frames", None), new_sites=True)
         if self.subm:
             return x.shadow(out)
-        return x.shadow(out, e.out_indices, e.out_shape, e.out_table, e.n_out)
+        return x.shadow(out, e.out_indices, e.out_shape, e.out_table, e.n_out, seg=e.seg_out,
+                        frames=getattr(e, "out_frames", None), new_sites=True)
 
 
 class SubMConv3d(SparseConvolution):
@@ -246,7 +283,13 @@ class SparseSequential(nn.Sequential):
                 x = m(x)
             elif isinstance(x, SparseConvTensor):
                 if x.n > 0:
-                    x = x.shadow(m(x.features))
+                    if (x.seg is not None and len(x.seg) > 1 and isinstance(m, nn.modules.batchnorm._BatchNorm)
+                            and m.training):
+                        # the reference normalises every frame with its own batch statistics (one encoder
+                        # call per frame) and updates the running statistics frame after frame
+                        x = x.shadow(torch.cat([m(f) for f in torch.split(x.features, x.seg)], dim=0))
+                    else:
+                        x = x.shadow(m(x.features))
             else:
                 x = m(x)
         return x

@@ -24,52 +24,92 @@ def get_middle_class(name):
     return REGISTERED_MIDDLE_CLASSES[name]
 
 
+_GEOMS = [("conv3d2", (3, 3, 3), (2, 2, 2), (1, 1, 1)), ("conv3d3", (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+          ("conv3d4", (3, 3, 3), (2, 2, 2), (0, 1, 1)), ("conv3d5", (3, 1, 1), (2, 1, 1), (0, 0, 0))]
+_SUBM_KEYS = ["subm0", "subm1", "subm2", "subm3"]
+
+
+def _enqueue_frame_tables(indices, n, sparse_shape, table0, caps):
+    """Enqueue every table kernel of one frame (no host round trip: the row counts of the deeper levels stay
+    on the device while the next level is built).  -> (levels, raw tables)."""
+    tab = table0 if table0 is not None else K.site_table_build(indices, n, sparse_shape)
+    lv = [dict(idx=indices, cap=n, ndev=None, shape=list(sparse_shape), tab=tab)]
+    raw = {}
+    for li, (key, ks, st, pd) in enumerate(_GEOMS):
+        cur = lv[-1]
+        raw[_SUBM_KEYS[li]] = K.subm_table(cur["idx"], cur["cap"], cur["tab"], (3, 3, 3), n_dev=cur["ndev"])
+        cap = None if caps is None else caps[li]
+        if cap is None:
+            # typical LiDAR levels shrink; overflow is detected by the caller and retried exactly
+            cells = int(np.prod(K.out_shape_of(cur["shape"], ks, st, pd)))
+            cap = max(1, min(cur["cap"], cells))
+        otab, oc, ndev2, nbr, nbr_inv = K.strided_table(cur["idx"], cur["cap"], cur["shape"], ks, st, pd,
+                                                        n_dev=cur["ndev"], out_cap=cap)
+        raw[key] = (nbr, nbr_inv)
+        lv.append(dict(idx=oc, cap=cap, ndev=ndev2[:1], shape=list(otab.shape), tab=otab, ndev2=ndev2))
+    return lv, raw
+
+
+def _frames_tables(frames, sparse_shape):
+    """frames: list of (indices, n, table0).  All frames are enqueued first and ONE device->host copy brings
+    back every level count.  -> per frame (levels, raw tables, row counts per level)."""
+    pend = [_enqueue_frame_tables(idx, n, sparse_shape, tab, None) for idx, n, tab in frames]
+    counts = torch.stack([torch.stack([l["ndev2"] for l in lv[1:]]) for lv, _ in pend]).cpu().numpy()
+    out = []
+    for f, (lv, raw) in enumerate(pend):
+        c = counts[f]
+        while not (c[:, 1] <= [l["cap"] for l in lv[1:]]).all():        # rare: a level grew; redo this frame
+            caps = [max(int(v), 1) * 2 for v in c[:, 1]]
+            lv, raw = _enqueue_frame_tables(frames[f][0], frames[f][1], sparse_shape, frames[f][2], caps)
+            c = torch.stack([l["ndev2"] for l in lv[1:]]).cpu().numpy()
+        out.append((lv, raw, [frames[f][1]] + [int(v) for v in c[:, 0]]))
+    return out
+
+
 def build_frame_tables(indices, n, sparse_shape, table0=None):
-    """All index tables of SpMiddleFHDWithCov2_3 for one frame, enqueued without a host round trip
-    (row counts of the deeper levels stay on the device while the next level is built) and finished
-    by ONE device->host copy of the four counts.  Returns {indice_key: IndexEntry}."""
-    geoms = [("conv3d2", (3, 3, 3), (2, 2, 2), (1, 1, 1)), ("conv3d3", (3, 3, 3), (2, 2, 2), (1, 1, 1)),
-             ("conv3d4", (3, 3, 3), (2, 2, 2), (0, 1, 1)), ("conv3d5", (3, 1, 1), (2, 1, 1), (0, 0, 0))]
-    subm_keys = ["subm0", "subm1", "subm2", "subm3"]
-    caps = None
-    while True:
-        tab = table0 if table0 is not None else K.site_table_build(indices, n, sparse_shape)
-        lv = [dict(idx=indices, cap=n, ndev=None, shape=list(sparse_shape), tab=tab)]
-        raw = {}
-        for li, (key, ks, st, pd) in enumerate(geoms):
-            cur = lv[-1]
-            raw[subm_keys[li]] = K.subm_table(cur["idx"], cur["cap"], cur["tab"], (3, 3, 3), n_dev=cur["ndev"])
-            cap = None if caps is None else caps[li]
-            if cap is None:
-                # typical LiDAR levels shrink; overflow is detected below and retried exactly
-                cells = int(np.prod(K.out_shape_of(cur["shape"], ks, st, pd)))
-                cap = max(1, min(cur["cap"], cells))
-            otab, oc, ndev2, nbr, nbr_inv = K.strided_table(cur["idx"], cur["cap"], cur["shape"], ks, st, pd,
-                                                            n_dev=cur["ndev"], out_cap=cap)
-            raw[key] = (nbr, nbr_inv)
-            lv.append(dict(idx=oc, cap=cap, ndev=ndev2[:1], shape=list(otab.shape), tab=otab, ndev2=ndev2))
-        counts = torch.stack([l["ndev2"] for l in lv[1:]]).cpu().numpy()    # the frame's only sync
-        if (counts[:, 1] <= [l["cap"] for l in lv[1:]]).all():
-            break
-        caps = [int(c) for c in counts[:, 1]]
-        caps = [max(int(c), 1) * 2 for c in counts[:, 1]]
-    ns = [n] + [int(c) for c in counts[:, 0]]
+    """All index tables of SpMiddleFHDWithCov2_3 for one frame.  Returns {indice_key: IndexEntry}."""
+    return build_tables_batched([(indices, n, table0)], sparse_shape)[0]
+
+
+def build_tables_batched(frames, sparse_shape):
+    """Index tables for T frames that share one pass through the encoder: per-frame tables are appended
+    row-wise (row indices of frame f shifted by the rows before it).  -> ({indice_key: IndexEntry}, meta)."""
+    per = _frames_tables(frames, sparse_shape)
+    T = len(per)
+    ns = [[p[2][l] for p in per] for l in range(5)]                    # rows per level per frame
+    offs = [[int(sum(ns[l][:f])) for f in range(T)] for l in range(5)]
+    tot = [int(sum(ns[l])) for l in range(5)]
+
+    def level_frames(l):
+        return [(offs[l][f], ns[l][f], per[f][0][l]["tab"], per[f][0][l]["idx"]) for f in range(T)]
+
+    def cat(tabs, l_rows, l_vals):
+        if T == 1:
+            return tabs[0]
+        return K.table_concat(tabs, ns[l_rows], offs[l_vals])
+
     entries = {}
     for li in range(4):
-        l = lv[li]
-        nbr = raw[subm_keys[li]]
-        entries[subm_keys[li]] = IndexEntry("subm", nbr, nbr, ns[li], ns[li], l["idx"], l["shape"], l["tab"], True)
-    for li, (key, ks, st, pd) in enumerate(geoms):
-        nbr, nbr_inv = raw[key]
-        o = lv[li + 1]
-        e = IndexEntry("strided", nbr, nbr_inv, ns[li], ns[li + 1], o["idx"], o["shape"], o["tab"], False)
-        e.in_indices, e.in_shape, e.in_table = lv[li]["idx"], lv[li]["shape"], lv[li]["tab"]
+        nbr = cat([p[1][_SUBM_KEYS[li]] for p in per], li, li)
+        e = IndexEntry("subm", nbr, nbr, tot[li], tot[li], per[0][0][li]["idx"] if T == 1 else None,
+                       per[0][0][li]["shape"], per[0][0][li]["tab"] if T == 1 else None, True)
+        e.seg_in = e.seg_out = ns[li]
+        entries[_SUBM_KEYS[li]] = e
+    for li, (key, ks, st, pd) in enumerate(_GEOMS):
+        nbr = cat([p[1][key][0] for p in per], li + 1, li)             # out rows -> in rows
+        nbr_inv = cat([p[1][key][1] for p in per], li, li + 1)         # in rows -> out rows
+        o0, i0 = per[0][0][li + 1], per[0][0][li]
+        e = IndexEntry("strided", nbr, nbr_inv, tot[li], tot[li + 1], o0["idx"] if T == 1 else None, o0["shape"],
+                       o0["tab"] if T == 1 else None, False)
+        e.in_indices, e.in_shape, e.in_table = (i0["idx"] if T == 1 else None), i0["shape"], (i0["tab"] if T == 1 else None)
+        e.seg_in, e.seg_out = ns[li], ns[li + 1]
+        e.in_frames, e.out_frames = level_frames(li), level_frames(li + 1)
         entries[key] = e
     # decoder keys are new names for site sets that already have tables (middle.py:181-213)
     entries["dsubm3"] = entries["subm1"]
     entries["dsubm2"] = entries["subm0"]
     entries["dsubm1"] = entries["subm0"]
-    return entries
+    return entries, {"rows": ns, "offsets": offs, "frames0": level_frames(0)}
 
 
 @register_middle
@@ -126,18 +166,30 @@ class SpMiddleFHDWithCov2_3(nn.Module):
         self.max_batch_size = 6
 
     def forward(self, voxel_features, coors, batch_size, table0=None):
+        rets, covs = self.forward_frames([voxel_features], [coors], batch_size, [table0])
+        return rets[0], covs[0]
+
+    def forward_frames(self, voxel_features, coors, batch_size, tables=None):
+        """The reference calls the encoder once per frame (`voxel_odom_net.py:423-428`); here the T frames
+        of an example share ONE pass: their rows are concatenated, every sparse convolution runs once on
+        T times the rows (frames never mix: each frame's tables only reference its own rows), batch
+        statistics of the covariance decoder's BatchNorm1d stay per frame.  -> ([bev_t], [cov_t])."""
         assert batch_size == 1, "Only support batch_size=1 for now"
-        coors = coors.int().contiguous()
-        n = int(voxel_features.shape[0])
-        ret = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size, table=table0)
-        ret.indice_dict = build_frame_tables(coors, n, [int(s) for s in self.sparse_shape], table0)
-        ret.table = ret.indice_dict["subm0"].out_table
+        T = len(voxel_features)
+        tables = tables if tables is not None else [None] * T
+        coors = [c.int().contiguous() for c in coors]
+        shape = [int(s) for s in self.sparse_shape]
+        frames = [(coors[t], int(voxel_features[t].shape[0]), tables[t]) for t in range(T)]
+        entries, meta = build_tables_batched(frames, shape)
+        feats = voxel_features[0] if T == 1 else torch.cat(voxel_features, dim=0)
+        ret = spconv.SparseConvTensor(feats, coors[0] if T == 1 else None, self.sparse_shape, batch_size,
+                                      table=entries["subm0"].out_table)
+        ret.indice_dict = entries
+        ret.seg, ret.frames = meta["rows"][0], meta["frames0"]
         ret0 = self.middle_conv(ret)
         ret = self.middle_conv_tail(ret0)
         cov_pred = self.middle_cov_deconv(ret0)
         cov = cov_pred.features
         cov = torch.cat([F.elu(cov[:, :3]) + 1 + 1e-6, cov[:, 3:]], dim=1)     # middle.py:237
-        ret = ret.dense()
-        N, C, D, H, W = ret.shape
-        ret = ret.view(N, C * D, H, W)
-        return ret, cov
+        covs = [cov] if T == 1 else list(torch.split(cov, meta["rows"][0]))
+        return ret.dense_frames(), covs

@@ -216,11 +216,16 @@ class UnVoxelOdomNetICP3(nn.Module):
         voxel_features = [self.voxel_feature_extractor(voxels[i], num_points[i], coors[i]) for i in range(len(voxels))]
         self.end_timer("voxel_feature_extractor")
         self.start_timer("middle forward")
-        spatial_features, middle_conf_preds = [], []
-        for i in range(len(voxel_features)):
-            ret, conf_pred = self.middle_feature_extractor(voxel_features[i], coors[i], batch_size, table0=tables[i])
-            spatial_features.append(ret)
-            middle_conf_preds.append(conf_pred)
+        if hasattr(self.middle_feature_extractor, "forward_frames"):
+            # all frames of the example share one pass through the sparse encoder
+            spatial_features, middle_conf_preds = self.middle_feature_extractor.forward_frames(
+                voxel_features, coors, batch_size, tables)
+        else:
+            spatial_features, middle_conf_preds = [], []
+            for i in range(len(voxel_features)):
+                ret, conf_pred = self.middle_feature_extractor(voxel_features[i], coors[i], batch_size)
+                spatial_features.append(ret)
+                middle_conf_preds.append(conf_pred)
         self.end_timer("middle forward")
         preds_dict = self.odom_predictor(spatial_features, tq_map_gt=None)
         if self.training or self.testing:

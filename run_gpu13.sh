@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/pytest_all.log
+grep -E "^E  |FAILED|passed|failed|Error" gpurun_out/pytest_all.log | head -40
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err
+cut -c1-400 gpurun_out/bench.log; tail -3 gpurun_out/bench.err | cut -c1-300
+timeout 600 python scripts/profile_step.py --pairs 2 > gpurun_out/profile_step.txt 2>&1
+grep -E "wall ms|profiler:|Self CUDA time total" gpurun_out/profile_step.txt
