@@ -174,6 +174,10 @@ int rslo_kabsch(const float* src, const float* tgt, const int32_t* tgt_idx, cons
                 float* R_out, float* t_out, float* comp_R, float* comp_t, void* workspace, size_t workspace_bytes,
                 rslo_stream_t stream);
 
+/* ROI threshold (losses.py:326-334): out[0] = max(k-th smallest of values[0..n), floor_value), k 1-based;
+ * replaces torch.kthvalue + torch.max and keeps the threshold on the device. */
+int rslo_kth_threshold(const float* values, int n, int k, float floor_value, float* out, rslo_stream_t stream);
+
 /* ---- a11: covariance-weighted residual of the consistency loss (losses.py:348-363, 401-435) --------
  * pred [n,3], target [m,3], idx [n] (association into target), cov_pred [n,7], cov_target [m,7] raw
  * covariance parameters (3 eigenvalue increments + quaternion x,y,z,w), R [9] detached predicted rotation,

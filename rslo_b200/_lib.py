@@ -49,6 +49,7 @@ SIGNATURES = {
     "rslo_dense_from_sites": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rslo_kabsch_workspace_bytes": (_sz, []),
     "rslo_kabsch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rslo_kth_threshold": (_i, [_vp, _i, _i, _f, _vp, _vp]),
     "rslo_cov_residual_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     "rslo_cov_residual_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp]),

@@ -82,9 +82,8 @@ class Aleat5_1ChamferL2NormalWeightedALLSVDLoss(Loss):
 
     def _roi_threshold(self, dist):
         """kth value at the penalize_ratio quantile, floored at 1.0 (`losses.py:326-334`)."""
-        flat = dist.reshape(-1)
-        m, _ = torch.kthvalue(flat, 1 + int(flat.numel() * self.penalize_ratio), dim=-1)
-        return torch.max(m, torch.ones_like(m))
+        n = dist.numel()
+        return K.kth_threshold(dist, 1 + int(n * self.penalize_ratio), 1.0)
 
     def _compute_loss(self, xyz_pred, xyz_target, cov_pred, cov_target, R_pred, t_pred, normal_pred,
                       normal_target, mask=None, alpha=None, focal_gamma=None, icp_iter=1):

@@ -404,6 +404,16 @@ def kabsch(src, tgt, weight=None, mask=None, dist=None, dist_threshold=None, com
     return R, t
 
 
+def kth_threshold(values, k, floor_value):
+    """max(k-th smallest of values, floor_value) -> [1] on the device (losses.py:326-334), no host sync."""
+    v = _f32(values.contiguous().reshape(-1))
+    out = torch.empty(1, dtype=torch.float32, device=v.device)
+    check(lib.rslo_kth_threshold(ptr(v), v.numel(), int(k), float(floor_value), ptr(out), stream()),
+          "rslo_kth_threshold")
+    _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # a11: covariance-weighted residual (fused forward / backward)
 # ------------------------------------------------------------------------------------------------

@@ -29,11 +29,11 @@ _GEOMS = [("conv3d2", (3, 3, 3), (2, 2, 2), (1, 1, 1)), ("conv3d3", (3, 3, 3), (
 _SUBM_KEYS = ["subm0", "subm1", "subm2", "subm3"]
 
 
-def _enqueue_frame_tables(indices, n, sparse_shape, table0, caps):
+def _enqueue_frame_tables(indices, n, sparse_shape, table0, caps, n_dev=None):
     """Enqueue every table kernel of one frame (no host round trip: the row counts of the deeper levels stay
     on the device while the next level is built).  -> (levels, raw tables)."""
     tab = table0 if table0 is not None else K.site_table_build(indices, n, sparse_shape)
-    lv = [dict(idx=indices, cap=n, ndev=None, shape=list(sparse_shape), tab=tab)]
+    lv = [dict(idx=indices, cap=n, ndev=n_dev, shape=list(sparse_shape), tab=tab)]
     raw = {}
     for li, (key, ks, st, pd) in enumerate(_GEOMS):
         cur = lv[-1]
@@ -51,24 +51,32 @@ def _enqueue_frame_tables(indices, n, sparse_shape, table0, caps):
 
 
 def _frames_tables(frames, sparse_shape):
-    """frames: list of (indices, n, table0).  All frames are enqueued first and ONE device->host copy brings
-    back every level count.  -> per frame (levels, raw tables, row counts per level)."""
-    pend = [_enqueue_frame_tables(idx, n, sparse_shape, tab, None) for idx, n, tab in frames]
-    counts = torch.stack([torch.stack([l["ndev2"] for l in lv[1:]]) for lv, _ in pend]).cpu().numpy()
+    """frames: list of (indices, n, table0, n_dev): n rows are live, or - when n_dev (device int) is given -
+    n is only the capacity and the live count is still on the device (voxeliser output that has not been
+    synchronised).  All frames are enqueued first and ONE device->host copy brings back every count.
+    -> per frame (levels, raw tables, row counts per level)."""
+    pend = [_enqueue_frame_tables(idx, n, sparse_shape, tab, None, nd) for idx, n, tab, nd in frames]
+    dev = frames[0][0].device
+
+    def counts_of(lv, nd, n):
+        n0 = nd.reshape(1).to(torch.int32) if nd is not None else torch.tensor([n], dtype=torch.int32, device=dev)
+        return torch.cat([torch.stack([n0[0], n0[0]])[None], torch.stack([l["ndev2"] for l in lv[1:]])])
+
+    counts = torch.stack([counts_of(lv, fr[3], fr[1]) for (lv, _), fr in zip(pend, frames)]).cpu().numpy()
     out = []
     for f, (lv, raw) in enumerate(pend):
         c = counts[f]
-        while not (c[:, 1] <= [l["cap"] for l in lv[1:]]).all():        # rare: a level grew; redo this frame
-            caps = [max(int(v), 1) * 2 for v in c[:, 1]]
-            lv, raw = _enqueue_frame_tables(frames[f][0], frames[f][1], sparse_shape, frames[f][2], caps)
-            c = torch.stack([l["ndev2"] for l in lv[1:]]).cpu().numpy()
-        out.append((lv, raw, [frames[f][1]] + [int(v) for v in c[:, 0]]))
+        while not (c[1:, 1] <= [l["cap"] for l in lv[1:]]).all():       # rare: a level grew; redo this frame
+            caps = [max(int(v), 1) * 2 for v in c[1:, 1]]
+            lv, raw = _enqueue_frame_tables(frames[f][0], frames[f][1], sparse_shape, frames[f][2], caps, frames[f][3])
+            c = counts_of(lv, frames[f][3], frames[f][1]).cpu().numpy()
+        out.append((lv, raw, [int(v) for v in c[:, 0]]))
     return out
 
 
 def build_frame_tables(indices, n, sparse_shape, table0=None):
     """All index tables of SpMiddleFHDWithCov2_3 for one frame.  Returns {indice_key: IndexEntry}."""
-    return build_tables_batched([(indices, n, table0)], sparse_shape)[0]
+    return build_tables_batched([(indices, n, table0, None)], sparse_shape)[0]
 
 
 def build_tables_batched(frames, sparse_shape):
@@ -166,21 +174,27 @@ class SpMiddleFHDWithCov2_3(nn.Module):
         self.max_batch_size = 6
 
     def forward(self, voxel_features, coors, batch_size, table0=None):
-        rets, covs = self.forward_frames([voxel_features], [coors], batch_size, [table0])
+        rets, covs, _, _ = self.forward_frames([voxel_features], [coors], batch_size, [table0])
         return rets[0], covs[0]
 
-    def forward_frames(self, voxel_features, coors, batch_size, tables=None):
+    def forward_frames(self, voxel_features, coors, batch_size, tables=None, n_devs=None):
         """The reference calls the encoder once per frame (`voxel_odom_net.py:423-428`); here the T frames
         of an example share ONE pass: their rows are concatenated, every sparse convolution runs once on
         T times the rows (frames never mix: each frame's tables only reference its own rows), batch
-        statistics of the covariance decoder's BatchNorm1d stay per frame.  -> ([bev_t], [cov_t])."""
+        statistics of the covariance decoder's BatchNorm1d stay per frame.
+        `n_devs[t]` (device int) marks frame t's inputs as capacity-sized with the live row count still on the
+        device; the counts of all frames and levels come back in one copy.
+        -> ([bev_t], [cov_t], [features_t], [coors_t]) with the inputs trimmed to their live rows."""
         assert batch_size == 1, "Only support batch_size=1 for now"
         T = len(voxel_features)
         tables = tables if tables is not None else [None] * T
+        n_devs = n_devs if n_devs is not None else [None] * T
         coors = [c.int().contiguous() for c in coors]
         shape = [int(s) for s in self.sparse_shape]
-        frames = [(coors[t], int(voxel_features[t].shape[0]), tables[t]) for t in range(T)]
+        frames = [(coors[t], int(voxel_features[t].shape[0]), tables[t], n_devs[t]) for t in range(T)]
         entries, meta = build_tables_batched(frames, shape)
+        voxel_features = [voxel_features[t][:meta["rows"][0][t]] for t in range(T)]
+        coors = [coors[t][:meta["rows"][0][t]] for t in range(T)]
         feats = voxel_features[0] if T == 1 else torch.cat(voxel_features, dim=0)
         ret = spconv.SparseConvTensor(feats, coors[0] if T == 1 else None, self.sparse_shape, batch_size,
                                       table=entries["subm0"].out_table)
@@ -192,4 +206,4 @@ class SpMiddleFHDWithCov2_3(nn.Module):
         cov = cov_pred.features
         cov = torch.cat([F.elu(cov[:, :3]) + 1 + 1e-6, cov[:, 3:]], dim=1)     # middle.py:237
         covs = [cov] if T == 1 else list(torch.split(cov, meta["rows"][0]))
-        return ret.dense_frames(), covs
+        return ret.dense_frames(), covs, voxel_features, coors

@@ -206,20 +206,21 @@ class UnVoxelOdomNetICP3(nn.Module):
         out = K.voxelize(points, vg.voxel_size, vg.point_cloud_range, vg.grid_size, max_points=vg.max_num_points,
                          max_voxels=vg.max_voxels_per_call, block_factor=vg.block_factor, block_size=vg.block_size,
                          height_threshold=vg.height_threshold, materialize=False, with_mean=True, with_table=True)
-        n = int(out["n_dev"].item())
-        return out["mean"][:n], out["coordinates"][:n], out["num_points_per_voxel"][:n], out["table"]
+        # capacity-sized outputs; the live count stays on the device until the encoder's single count copy
+        return out["mean"], out["coordinates"], out["num_points_per_voxel"], out["table"], out["n_dev"]
 
     def network_forward(self, voxels, num_points, coors, batch_size, example):
         assert len(voxels) == len(num_points) == len(coors), "The lengths should be same."
         tables = example.get("_site_tables", [None] * len(voxels))
+        n_devs = example.get("_n_dev", None)
         self.start_timer("voxel_feature_extractor")
         voxel_features = [self.voxel_feature_extractor(voxels[i], num_points[i], coors[i]) for i in range(len(voxels))]
         self.end_timer("voxel_feature_extractor")
         self.start_timer("middle forward")
         if hasattr(self.middle_feature_extractor, "forward_frames"):
             # all frames of the example share one pass through the sparse encoder
-            spatial_features, middle_conf_preds = self.middle_feature_extractor.forward_frames(
-                voxel_features, coors, batch_size, tables)
+            spatial_features, middle_conf_preds, voxel_features, coors = self.middle_feature_extractor.forward_frames(
+                voxel_features, coors, batch_size, tables, n_devs)
         else:
             spatial_features, middle_conf_preds = [], []
             for i in range(len(voxel_features)):
@@ -241,15 +242,17 @@ class UnVoxelOdomNetICP3(nn.Module):
 
     def forward(self, example):
         if "points" in example:
-            voxels, num_points, coors, tables = [], [], [], []
+            voxels, num_points, coors, tables, n_devs = [], [], [], [], []
             for pts in example["points"]:
-                m, c, npts, tab = self._voxelize_on_device(pts)
+                m, c, npts, tab, nd = self._voxelize_on_device(pts)
                 voxels.append(m)
                 coors.append(c)
                 num_points.append(npts)
                 tables.append(tab)
+                n_devs.append(nd)
             example = dict(example)
             example["_site_tables"] = tables
+            example["_n_dev"] = n_devs
             batch_size_dev = 1
         else:
             voxels, num_points, coors = example["voxels"], example["num_points"], example["coordinates"]

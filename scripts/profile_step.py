@@ -62,10 +62,10 @@ def sync_time(fn, n=5):
 ms, vox = sync_time(lambda: [net._voxelize_on_device(p) for p in (a, b)])
 print(f"stage voxelize x2 frames: {ms:.2f} ms")
 def enc():
-    return [net.middle_feature_extractor(v[0], v[1], 1, table0=v[3]) for v in vox]
+    return net.middle_feature_extractor.forward_frames([v[0] for v in vox], [v[1] for v in vox], 1, [v[3] for v in vox], [v[4] for v in vox])
 ms, encs = sync_time(enc)
 print(f"stage sparse encoder fwd x2 frames: {ms:.2f} ms")
-ms, head = sync_time(lambda: net.odom_predictor([e[0] for e in encs]))
+ms, head = sync_time(lambda: net.odom_predictor(list(encs[0])))
 print(f"stage head fwd: {ms:.2f} ms")
 
 from torch.profiler import ProfilerActivity, profile

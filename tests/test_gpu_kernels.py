@@ -323,3 +323,16 @@ def test_kabsch_fused_gather_and_weights(K):
     R2, t2 = K.kabsch(src, assoc, weight=(w * w).contiguous(), dist=dist, dist_threshold=thr)
     np.testing.assert_allclose(R1.cpu().numpy(), R2.cpu().numpy(), atol=1e-5)
     np.testing.assert_allclose(t1.cpu().numpy(), t2.cpu().numpy(), atol=1e-4)
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 40000, 123457])
+def test_kth_threshold_matches_torch(K, n):
+    g = torch.Generator().manual_seed(n)
+    d = (torch.rand(n, generator=g) * 4).pow(2).cuda()
+    d[::3] = d[0].clone()                                # ties
+    for ratio in (0.97, 0.5, 0.0):
+        k = min(n, 1 + int(n * ratio))
+        want = torch.max(torch.kthvalue(d, k).values, torch.ones((), device="cuda"))
+        got = K.kth_threshold(d, k, 1.0)
+        assert float(got) == float(want)
+    assert float(K.kth_threshold(d, n, 0.0)) == float(d.max())
