@@ -22,115 +22,15 @@
 // (double-buffered TMEM accumulator: MMA <-> drain warps).  Two 48 KB stages per CTA, two CTAs per SM
 // (measured faster than four stages with one CTA per SM: 51 vs 58 us on the 19.6k-row 64->64 layer).
 // Small levels are split over gridDim.y CTAs per tile (disjoint offsets) so all 148 SMs have work.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace rslo {
 namespace {
+using namespace tc;
 
 constexpr int TC_ROWS = 128;
 constexpr int TC_PRODUCERS = 128;          // warps 0..3: gather
 constexpr int TC_THREADS = 288;            // + warp 4: TMEM owner and MMA issuer; warps 5..8: drain + epilogue
-constexpr unsigned TC_SPIN_LIMIT = 1u << 28;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded wait: a broken pipeline traps (sticky launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    for (unsigned spin = 0;; ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (spin > TC_SPIN_LIMIT) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows are 128 B (32 fp32), 8-row groups are
-// 1024 B apart (SBO), LBO = 1 (unused by swizzled K-major), descriptor version 1 (Blackwell).
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n)
-{
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
-{
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// byte offset of element (row, col) inside a [rows x KDIM] fp32 operand stored as KDIM/32 blocks of
-// [rows x 32] in the canonical K-major SWIZZLE_128B layout
-__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows)
-{
-    const int kb = col >> 5, c16 = (col & 31) >> 2, r8 = row & 7;
-    return (uint32_t)kb * (uint32_t)(rows * 128) + (uint32_t)(row >> 3) * 1024u + (uint32_t)r8 * 128u +
-           (uint32_t)((c16 ^ r8) << 4) + (uint32_t)(col & 3) * 4u;
-}
-
-__device__ __forceinline__ void sts128(uint32_t addr, const float4& v)
-{
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-// round-to-nearest (ties away) onto TF32's 10-bit mantissa; the carry may ripple into the exponent
-__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // ---- weight prep: W [K,Cin,Cout] -> per-offset images {B_hi, B_lo}, B is [NDIM x KDIM] K-major ----
 //   forward      (transpose = 0): NDIM = Cout, KDIM = Cin,  B(n, kk) = W[k][kk][n]

@@ -346,6 +346,20 @@ def spconv_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=T
     return gw, gb
 
 
+@_profiled("spconv_tc_wgrad", _cost_spconv_bwd_weight)
+def spconv_tc_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=False):
+    """dW on the tcgen05 tensor cores (split-TF32); Cin, Cout in {32, 64}."""
+    feat = _f32(feat)
+    g = _f32(grad_out.contiguous())
+    nbr = _i32(nbr)
+    Cin, Cout = weight_shape[-2], weight_shape[-1]
+    gw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=g.device)
+    check(lib.rslo_spconv_tc_backward_weight(ptr(feat), ptr(g), ptr(nbr), n_out, None, nbr.shape[1], Cin, Cout,
+                                             ptr(gw), stream()), "rslo_spconv_tc_backward_weight")
+    _count()
+    return gw
+
+
 def act_backward(grad_out, out, act, slope, need_bias=True):
     """LeakyReLU backward from the saved output fused with the bias gradient -> (grad_act, grad_bias)."""
     g = _f32(grad_out.contiguous())

@@ -162,7 +162,10 @@ class _SpConvFn(torch.autograd.Function):
             else:
                 gi = K.spconv_backward_data(g, nbr_t, n_in, weight, e.mirror)
         if ctx.needs_input_grad[1]:
-            gw, _ = K.spconv_backward_weight(feat, g, nbr, n_out, weight.shape, need_bias=False)
+            if ctx.tc:
+                gw = K.spconv_tc_backward_weight(feat, g, nbr, n_out, weight.shape)
+            else:
+                gw, _ = K.spconv_backward_weight(feat, g, nbr, n_out, weight.shape, need_bias=False)
         return gi, gw, gb_fused, None, None, None, None
 
 

@@ -336,3 +336,26 @@ def test_kth_threshold_matches_torch(K, n):
         got = K.kth_threshold(d, k, 1.0)
         assert float(got) == float(want)
     assert float(K.kth_threshold(d, n, 0.0)) == float(d.max())
+
+
+@pytest.mark.parametrize("cin,cout,K_,n_out", [(64, 64, 27, 2577), (32, 32, 27, 2577), (32, 64, 27, 2577),
+                                               (64, 32, 27, 2577), (64, 64, 3, 2577), (64, 64, 27, 39188),
+                                               (64, 64, 27, 50)])
+def test_spconv_tensor_core_wgrad(K, cin, cout, K_, n_out):
+    """tcgen05 weight-gradient kernel (MN-major operands, offsets stacked along M) vs autograd of the oracle."""
+    g = torch.Generator().manual_seed(cin * 7 + cout + K_ + n_out)
+    n_in = 3000
+    nbr = torch.randint(0, n_in, (n_out, K_), generator=g, dtype=torch.int32)
+    nbr[torch.rand((n_out, K_), generator=g) < 0.6] = -1
+    feat = torch.randn((n_in, cin), generator=g)
+    w = (torch.randn((K_, cin, cout), generator=g) * 0.1).requires_grad_(True)
+    o = osp.gather_conv(feat, nbr, w)
+    go = torch.randn(o.shape, generator=g)
+    o.backward(go)
+    gw = K.spconv_tc_backward_weight(feat.cuda(), go.cuda(), nbr.cuda(), n_out, (K_, cin, cout))
+    torch.cuda.synchronize()
+    ref = w.grad
+    err = (gw.cpu() - ref).abs().max().item()
+    print(f"tc wgrad max abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
+    # fp32 sums over up to ~4e4 rows in a different order (TMEM accumulation + atomics across CTAs)
+    assert err <= 2e-5 * ref.abs().max().item() + 1e-5
