@@ -227,7 +227,10 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
                 if (k < K) {
                     float* dst = dW + ((size_t)k * CIN + ci) * COUT + cb;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) atomicAdd(dst + i, v[i]);
+                    for (int i = 0; i < 16; i += 4)                  // 16-byte vector reductions (REDG.F32x4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                                     "f"(v[i + 2]), "f"(v[i + 3])
+                                     : "memory");
                 }
             }
         }

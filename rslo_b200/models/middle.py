@@ -177,7 +177,21 @@ class SpMiddleFHDWithCov2_3(nn.Module):
         rets, covs, _, _ = self.forward_frames([voxel_features], [coors], batch_size, [table0])
         return rets[0], covs[0]
 
-    def forward_frames(self, voxel_features, coors, batch_size, tables=None, n_devs=None):
+    def prepare_frames(self, voxel_features, coors, tables=None, n_devs=None):
+        """Index tables of all frames (+ the single device->host copy of the row counts) and the inputs
+        trimmed to their live rows.  Pure index work: can run ahead of time / on another stream."""
+        T = len(voxel_features)
+        tables = tables if tables is not None else [None] * T
+        n_devs = n_devs if n_devs is not None else [None] * T
+        coors = [c.int().contiguous() for c in coors]
+        shape = [int(s) for s in self.sparse_shape]
+        frames = [(coors[t], int(voxel_features[t].shape[0]), tables[t], n_devs[t]) for t in range(T)]
+        entries, meta = build_tables_batched(frames, shape)
+        feats = [voxel_features[t][:meta["rows"][0][t]] for t in range(T)]
+        coors = [coors[t][:meta["rows"][0][t]] for t in range(T)]
+        return {"entries": entries, "meta": meta, "features": feats, "coors": coors}
+
+    def forward_frames(self, voxel_features, coors, batch_size, tables=None, n_devs=None, prepared=None):
         """The reference calls the encoder once per frame (`voxel_odom_net.py:423-428`); here the T frames
         of an example share ONE pass: their rows are concatenated, every sparse convolution runs once on
         T times the rows (frames never mix: each frame's tables only reference its own rows), batch
@@ -186,15 +200,11 @@ class SpMiddleFHDWithCov2_3(nn.Module):
         device; the counts of all frames and levels come back in one copy.
         -> ([bev_t], [cov_t], [features_t], [coors_t]) with the inputs trimmed to their live rows."""
         assert batch_size == 1, "Only support batch_size=1 for now"
+        if prepared is None:
+            prepared = self.prepare_frames(voxel_features, coors, tables, n_devs)
+        entries, meta = prepared["entries"], prepared["meta"]
+        voxel_features, coors = prepared["features"], prepared["coors"]
         T = len(voxel_features)
-        tables = tables if tables is not None else [None] * T
-        n_devs = n_devs if n_devs is not None else [None] * T
-        coors = [c.int().contiguous() for c in coors]
-        shape = [int(s) for s in self.sparse_shape]
-        frames = [(coors[t], int(voxel_features[t].shape[0]), tables[t], n_devs[t]) for t in range(T)]
-        entries, meta = build_tables_batched(frames, shape)
-        voxel_features = [voxel_features[t][:meta["rows"][0][t]] for t in range(T)]
-        coors = [coors[t][:meta["rows"][0][t]] for t in range(T)]
         feats = voxel_features[0] if T == 1 else torch.cat(voxel_features, dim=0)
         ret = spconv.SparseConvTensor(feats, coors[0] if T == 1 else None, self.sparse_shape, batch_size,
                                       table=entries["subm0"].out_table)

@@ -47,6 +47,25 @@ def create_cycle_constraint_data(xs, cat_dim=1):
     return [torch.stack(x1, dim=cat_dim).reshape(-1, *shape[1:]), torch.stack(x2, dim=cat_dim).reshape(-1, *shape[1:])]
 
 
+def _record_stream_tree(obj, stream, _seen=None):
+    """Tell the caching allocator that every tensor reachable from `obj` is also used on `stream`."""
+    _seen = set() if _seen is None else _seen
+    if id(obj) in _seen or obj is None:
+        return
+    _seen.add(id(obj))
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream_tree(v, stream, _seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream_tree(v, stream, _seen)
+    elif hasattr(obj, "__dict__") and not isinstance(obj, (torch.nn.Module, torch.cuda.Stream, torch.cuda.Event)):
+        _record_stream_tree(vars(obj), stream, _seen)
+
+
 def _detach_tree(x, to_cpu=False):
     if isinstance(x, torch.Tensor):
         x = x.detach()
@@ -209,10 +228,43 @@ class UnVoxelOdomNetICP3(nn.Module):
         # capacity-sized outputs; the live count stays on the device until the encoder's single count copy
         return out["mean"], out["coordinates"], out["num_points_per_voxel"], out["table"], out["n_dev"]
 
+    # ---- ahead-of-time preparation (the reference voxelises in DataLoader workers, preprocess.py:493) ----
+    def prepare(self, example, inputs_ready=True):
+        """Voxelise `example["points"]` (device tensors, or pinned host tensors that are copied here) and
+        build every index table of the sparse encoder on a side stream, including the one device->host
+        copy of the row counts, so that the following `net(prepared)` neither waits for the main stream to
+        drain nor leaves it idle.  `inputs_ready=False` makes the side stream wait for work already queued on
+        the current stream (needed when the points were just produced there)."""
+        assert "points" in example, "prepare() takes the raw-scan input form"
+        dev = self.global_step.device
+        st = self.__dict__.get("_prep_stream")
+        if st is None:
+            st = self.__dict__["_prep_stream"] = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        if not inputs_ready:
+            st.wait_stream(main)
+        with torch.cuda.stream(st):
+            pts = [p.to(dev, non_blocking=True) if not p.is_cuda else p for p in example["points"]]
+            voxels, coors, tables, n_devs = [], [], [], []
+            for p in pts:
+                m, c, _, tab, nd = self._voxelize_on_device(p)
+                voxels.append(m)
+                coors.append(c)
+                tables.append(tab)
+                n_devs.append(nd)
+            prep = self.middle_feature_extractor.prepare_frames(voxels, coors, tables, n_devs)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        _record_stream_tree([prep, pts, voxels, coors], main)
+        out = dict(example)
+        out["_prepared"] = {"frames": prep, "event": ev}
+        return out
+
     def network_forward(self, voxels, num_points, coors, batch_size, example):
         assert len(voxels) == len(num_points) == len(coors), "The lengths should be same."
         tables = example.get("_site_tables", [None] * len(voxels))
         n_devs = example.get("_n_dev", None)
+        prepared = example.get("_prepared_frames", None)
         self.start_timer("voxel_feature_extractor")
         voxel_features = [self.voxel_feature_extractor(voxels[i], num_points[i], coors[i]) for i in range(len(voxels))]
         self.end_timer("voxel_feature_extractor")
@@ -220,7 +272,7 @@ class UnVoxelOdomNetICP3(nn.Module):
         if hasattr(self.middle_feature_extractor, "forward_frames"):
             # all frames of the example share one pass through the sparse encoder
             spatial_features, middle_conf_preds, voxel_features, coors = self.middle_feature_extractor.forward_frames(
-                voxel_features, coors, batch_size, tables, n_devs)
+                voxel_features, coors, batch_size, tables, n_devs, prepared=prepared)
         else:
             spatial_features, middle_conf_preds = [], []
             for i in range(len(voxel_features)):
@@ -241,7 +293,15 @@ class UnVoxelOdomNetICP3(nn.Module):
         return preds_dict
 
     def forward(self, example):
-        if "points" in example:
+        if "_prepared" in example:
+            prep = example["_prepared"]
+            torch.cuda.current_stream().wait_event(prep["event"])
+            example = dict(example)
+            example["_prepared_frames"] = prep["frames"]
+            voxels, coors = prep["frames"]["features"], prep["frames"]["coors"]
+            num_points = [None] * len(voxels)
+            batch_size_dev = 1
+        elif "points" in example:
             voxels, num_points, coors, tables, n_devs = [], [], [], [], []
             for pts in example["points"]:
                 m, c, npts, tab, nd = self._voxelize_on_device(pts)

@@ -146,3 +146,19 @@ def test_loss_stack_on_oracle_inputs(net):
     np.testing.assert_allclose(l.detach().cpu().numpy().reshape(-1), ref["C_loss"].reshape(-1), rtol=1e-4)
     np.testing.assert_allclose(res_r.cpu().numpy(), ref["res_r"], atol=1e-5)
     np.testing.assert_allclose(res_t.cpu().numpy(), ref["res_t"], atol=1e-5)
+
+
+def test_prepared_example_matches_direct_call(net):
+    """net.prepare() (voxelisation + tables on a side stream, ahead of time) changes nothing in the results."""
+    net, vg = net
+    g, frames, _ = _prep(net, "small_eval")
+    net.eval()
+    pts = [torch.from_numpy(f).cuda() for f in frames]
+    with torch.no_grad():
+        a = net({"points": pts})
+        ex = net.prepare({"points": pts})
+        ex2 = net.prepare({"points": [torch.from_numpy(f).pin_memory() for f in frames]})   # host scans
+        b = net(ex)
+        c = net(ex2)
+    for k in ("translation_preds", "rotation_preds", "tq_map_g"):
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
