@@ -252,8 +252,8 @@ def main():
                 outs.append(torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1))
             # the following pair is prepared while this one's kernels run
             prefetch["key"], prefetch["example"] = (idx + 1, from_host), prepared_example(idx + 1, from_host)
-        if train and world > 1:
-            reducer.all_reduce()
+        if train:
+            reducer.all_reduce()                    # pack into the flat buffer (+ NCCL all-reduce when N > 1)
         res = torch.cat([o.reshape(-1) for o in outs])
         if from_host:
             r = res.cpu()                                                  # D2H of the step's result

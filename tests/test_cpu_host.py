@@ -132,7 +132,7 @@ red.zero_()
 g = torch.Generator().manual_seed(100 + rank)          # each rank: its own shard of frame pairs
 x = torch.randn(4, 6, generator=g)
 net[2](net[1](net[0](x))).pow(2).sum().backward()      # net[3] gets no gradient (unused head parts)
-local_flat = red.flat.clone()
+local_flat = red.pack().clone()
 red.all_reduce()
 gathered = [torch.zeros_like(local_flat) for _ in range(world)]
 dist.all_gather(gathered, local_flat)
@@ -140,6 +140,8 @@ want = sum(gathered) / world
 assert torch.allclose(red.flat, want, atol=1e-6), (red.flat - want).abs().max()
 assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in net.parameters())
 assert float(net[3].weight.grad.abs().sum()) == 0.0
+red.zero_()
+assert all(p.grad is None for p in net.parameters())
 if rank == 0:
     print("OK", float(red.flat.abs().sum()))
 dist.destroy_process_group()
