@@ -310,7 +310,7 @@ def main():
 
     # roofline of the dominant kernel: profiled replica of the timed steps
     roofline, breakdown = None, None
-    if not args.no_profile and rank == 0:
+    if not args.no_profile:                  # every rank runs the replica (its steps contain the collective)
         K.PROFILE = []
         nprof = min(args.steps, 5)
         step(W, False)                       # fills the rulebook-size caches outside the measured calls
@@ -332,6 +332,7 @@ def main():
             a[2] += nbytes
             a[3] += flops
         K.PROFILE = None
+    if not args.no_profile and rank == 0:
         breakdown = {n: {"calls_per_step": a[0] / nprof, "ms_per_step": a[1] / nprof,
                          "share_of_step": a[1] / nprof / step_ms,
                          "algorithmic_GBps": a[2] / (a[1] * 1e-3) / 1e9 if a[1] > 0 else None}

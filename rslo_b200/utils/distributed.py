@@ -6,6 +6,7 @@ B200 design: the gradients are packed into ONE flat fp32 buffer by a single mult
 step's exchange is one in-place NCCL all-reduce over NVLink/NVSwitch (no per-tensor calls; ~0.15 ms at
 wire speed for 48 MB on 8 ranks), enqueued on the same stream right after backward.
 """
+import datetime
 import os
 
 import torch
@@ -24,9 +25,10 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local),
+                                    timeout=datetime.timedelta(seconds=180))
         else:
-            dist.init_process_group(backend, rank=rank, world_size=world)
+            dist.init_process_group(backend, rank=rank, world_size=world, timeout=datetime.timedelta(seconds=180))
     return rank, local, world
 
 
