@@ -169,6 +169,22 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for fn in sorted(os.listdir(pdir)):
+            if fn.endswith("_traffic.json"):
+                try:
+                    d = json.load(open(os.path.join(pdir, fn)))
+                    if kernel in d:
+                        best = d[kernel]["dram_bytes_per_launch_avg"]
+                except Exception:
+                    pass
+    return best
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -343,7 +359,7 @@ def main():
         nm, a = dom
         achieved = a[2] / (a[1] * 1e-3) / 1e9
         roofline = {"kernel": nm, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": measured_traffic(nm), "peak_source": peak_src,
                     "launches_per_step": a[0] / nprof, "avg_launch_ms": a[1] / a[0],
                     "algorithmic_bytes_per_launch": a[2] / a[0], "gflops_per_launch": a[3] / a[0] / 1e9,
                     "share_of_step": a[1] / nprof / step_ms}
