@@ -53,8 +53,10 @@ def workload_config(args):
                             "kitti_eval_ours model", "mode": "eval", "pairs_per_gpu": ppg, "beams": 64, "n_az": 1875}
     if args.workload == "stress":
         ppg = args.pairs_per_gpu or 1
-        return {"workload": "C5-shaped stress: 128 beams x 2344 az (300k rays), default 0.1 m grid, fwd+bwd",
-                "mode": "train", "pairs_per_gpu": ppg, "beams": 128, "n_az": 2344}
+        return {"workload": "C5 dense-scan stress: 128 beams x 2344 az (300k rays), voxel 0.05x0.05x0.2 m "
+                            "(grid 2816x1536x40, BEV 192x352), <=250000 voxels/frame, fwd+bwd",
+                "mode": "train", "pairs_per_gpu": ppg, "beams": 128, "n_az": 2344,
+                "config_path": os.path.join(ROOT, "rslo_b200", "config", "stress_005.prototxt")}
     ppg = args.pairs_per_gpu or 2
     return {"workload": "C3/C4 train fwd+bwd: 2 pairs per GPU, 120k-pt scans (64 beams x 1875 az), voxel 0.1x0.1x0.2 m, "
                         "<=40000 voxels/frame, kitti_train_ours model section, Chamfer+covariance loss, step>1500",
@@ -220,7 +222,7 @@ def main():
     train = cfg["mode"] == "train"
     ppg = cfg["pairs_per_gpu"]
 
-    net, vg = rslo_b200.build_network(testing=False, seed=7)
+    net, vg = rslo_b200.build_network(cfg.get("config_path"), testing=False, seed=7)
     onet.fill_weights(net, WEIGHT_SEED)
     net = net.to(dev)
     net.global_step.fill_(STEP_AFTER_WARMUP)

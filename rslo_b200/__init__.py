@@ -25,6 +25,10 @@ def build_network(config_path=None, testing=False, measure_time=False, seed=None
     from .builder import second_builder, voxel_builder
     cfg = _config.load(config_path or DEFAULT_CONFIG)
     vg = voxel_builder.build(cfg.model.second.voxel_generator)
+    try:        # preprocess.max_number_of_voxels of the input reader (dataset_builder.py:78, preprocess.py:493)
+        vg.max_voxels_per_call = int(cfg.train_input_reader.preprocess.max_number_of_voxels)
+    except AttributeError:
+        pass
     if seed is not None:
         torch.manual_seed(seed)
     net = second_builder.build(cfg.model.second, vg, measure_time=measure_time, testing=testing)

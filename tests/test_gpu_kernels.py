@@ -359,3 +359,35 @@ def test_spconv_tensor_core_wgrad(K, cin, cout, K_, n_out):
     print(f"tc wgrad max abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
     # fp32 sums over up to ~4e4 rows in a different order (TMEM accumulation + atomics across CTAs)
     assert err <= 2e-5 * ref.abs().max().item() + 1e-5
+
+
+def test_stress_grid_voxelize_and_rulebook_bit_exact(K):
+    """BASELINE config 5: 300k-ray scan, 0.05 x 0.05 x 0.1 m voxels (grid 2816 x 1536 x 80, 346 M cells),
+    up to 250000 voxels: voxel coordinates / counts and the first two levels of rulebooks, bit-exact."""
+    vs, grid = [0.05, 0.05, 0.1], [2816, 1536, 80]
+    pts = synthetic.make_pair(7, n_beams=128, n_az=2344)[0]
+    ref = onat.voxelize(pts, vs, RG, 10, 250000, 1, 8, -1.0)
+    out = K.voxelize(torch.from_numpy(pts).cuda(), vs, RG, grid, max_voxels=250000, materialize=False, with_table=True)
+    n = int(out["n_dev"].item())
+    assert n == len(ref["coordinates"]) and n > 100000
+    assert np.array_equal(out["coordinates"][:n, 1:].cpu().numpy(), ref["coordinates"])
+    assert np.array_equal(out["num_points_per_voxel"][:n].cpu().numpy(), ref["num_points_per_voxel"])
+    mean_ref = osp.vfe_mean(ref["voxels"], ref["num_points_per_voxel"]).numpy()
+    np.testing.assert_allclose(out["mean"][:n].cpu().numpy(), mean_ref, rtol=1e-5, atol=1e-6)
+    shape = [81, 1536, 2816]
+    co = ref["coordinates"]
+    coors4 = out["coordinates"][:n].contiguous()
+    nbr = K.subm_table(coors4, n, out["table"])
+    assert np.array_equal(nbr[:n].cpu().numpy(), onat.subm_table(co, shape))
+    tab1, c1, n1d, nb, nb_inv = K.strided_table(coors4, n, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    oc, oshape, rnb, rinv = onat.strided_table(co, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    n1 = int(n1d[0].item())
+    assert n1 == len(oc) and list(tab1.shape) == oshape
+    assert np.array_equal(c1[:n1, 1:].cpu().numpy(), oc)
+    assert np.array_equal(nb[:n1].cpu().numpy(), rnb) and np.array_equal(nb_inv[:n].cpu().numpy(), rinv)
+    # exact NN at this size: grid search == tiled brute force (both bit-identical to the reference formula)
+    q = out["mean"][:n, :3].contiguous()
+    t = (q + torch.tensor([0.9, 0.02, 0.0], device="cuda")).contiguous()
+    d1, i1 = K.nn_exact(q, t)
+    d2, i2 = K.nn_exact(q, t, brute=True)
+    assert torch.equal(i1, i2) and torch.equal(d1, d2)
