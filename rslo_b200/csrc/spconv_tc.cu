@@ -1,8 +1,8 @@
 // K4-TC: sparse 3-D convolution as an implicit GEMM on the 5th-gen tensor cores (sm_100a, tcgen05).
 //
-//   out[o,:] = act(bias + sum_k in[nbr[o,k],:] @ W[k])        Cin, Cout in {32, 64}
+//   out[o,:] = act(bias + sum_k in[nbr[o,k],:] @ W[k])        Cin, Cout in {32, 64, 128, 192, 256, 512}
 //
-// One CTA owns 128 output rows (one TMEM lane per row) and the full Cout.  For every kernel offset
+// One CTA owns 128 output rows (one TMEM lane per row) and a 64- (or 32-) wide slice of Cout (blockIdx.z).  For every kernel offset
 // k that at least one of its rows uses, the producer warps gather the 128 neighbour rows (zeros
 // where a row has no neighbour) into shared memory in the UMMA canonical K-major SWIZZLE_128B
 // layout, while the offset's weight tile arrives by one bulk async copy (TMA unit, cp.async.bulk)
@@ -36,7 +36,7 @@ constexpr int TC_THREADS = 288;            // + warp 4: TMEM owner and MMA issue
 //   forward      (transpose = 0): NDIM = Cout, KDIM = Cin,  B(n, kk) = W[k][kk][n]
 //   data-grad    (transpose = 1): NDIM = Cin,  KDIM = Cout, B(n, kk) = W[ks][n][kk], ks = mirror ? K-1-k : k
 __global__ void k_tc_prep(const float* __restrict__ W, int K, int Cin, int Cout, int transpose, int mirror,
-                          float* __restrict__ img)
+                          int ntile, float* __restrict__ img)
 {
     const int NDIM = transpose ? Cin : Cout, KDIM = transpose ? Cout : Cin;
     const int per = NDIM * KDIM;
@@ -47,12 +47,13 @@ __global__ void k_tc_prep(const float* __restrict__ W, int K, int Cin, int Cout,
     if (!transpose) v = W[((size_t)k * Cin + kk) * Cout + n];
     else v = W[((size_t)(mirror ? K - 1 - k : k) * Cin + n) * Cout + kk];
     const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
-    // image: per offset k, per 32-wide K block kb: {B_hi [NDIM x 32], B_lo [NDIM x 32]}, each SWIZZLE_128B K-major
-    const int kb = kk >> 5;
-    char* base = (char*)img + ((size_t)k * (KDIM / 32) + kb) * (size_t)(2 * NDIM * 128);
-    const uint32_t off = sw128_offset(n, kk & 31, NDIM);
+    // image: per N tile nt (ntile output channels), per offset k, per 32-wide K block kb:
+    //        {B_hi [ntile x 32], B_lo [ntile x 32]}, each SWIZZLE_128B K-major
+    const int kb = kk >> 5, nt = n / ntile, nn = n % ntile;
+    char* base = (char*)img + (((size_t)nt * K + k) * (KDIM / 32) + kb) * (size_t)(2 * ntile * 128);
+    const uint32_t off = sw128_offset(nn, kk & 31, ntile);
     *(float*)(base + off) = hi;
-    *(float*)(base + (size_t)NDIM * 128 + off) = lo;
+    *(float*)(base + (size_t)ntile * 128 + off) = lo;
 }
 
 constexpr int TC_KS = 32;                  // K channels staged per pipeline step (one 128-byte swizzle row)
@@ -77,7 +78,7 @@ template <int KDIM, int NDIM>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap, const int* n_dev, int K,
             const float* __restrict__ bimg, const float* __restrict__ bias, int act, float slope,
-            float* __restrict__ out, float* __restrict__ scratch, int* __restrict__ tile_counter)
+            float* __restrict__ out, int n_total, float* __restrict__ scratch, int* __restrict__ tile_counter)
 {
     using S = TcSmem<KDIM, NDIM>;
     extern __shared__ uint8_t smem_raw[];
@@ -98,6 +99,9 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     const int n = dev_count(n_dev, n_cap);
     const int row0 = blockIdx.x * TC_ROWS;
     const int split = gridDim.y, sidx = blockIdx.y;
+    const int ntile = blockIdx.z;             // this CTA's slice of NDIM output channels (n_total = gridDim.z * NDIM)
+    const int wtile = blockIdx.x * gridDim.z + ntile;          // work tile id (rows x channel slice)
+    bimg += (size_t)ntile * K * (KDIM / TC_KS) * (2 * S::B_BYTES / 4);
     if (row0 >= n) return;                    // uniform per CTA (all splits of the tile agree)
     constexpr int TCOLS = 2 * NDIM;           // two accumulator buffers (64 or 128 columns: powers of two)
 
@@ -274,12 +278,12 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         }
         bool finish = true;
         if (split > 1) {
-            float4* mine = reinterpret_cast<float4*>(scratch + ((size_t)(blockIdx.x * split + sidx) * TC_ROWS + r) * NDIM);
+            float4* mine = reinterpret_cast<float4*>(scratch + ((size_t)(wtile * split + sidx) * TC_ROWS + r) * NDIM);
 #pragma unroll
             for (int i = 0; i < NDIM; i += 4) mine[i / 4] = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
             __threadfence();
             drain_sync();
-            if (warp == 5 && lane == 0) *s_last = atomicAdd(tile_counter + blockIdx.x, 1) == split - 1;
+            if (warp == 5 && lane == 0) *s_last = atomicAdd(tile_counter + wtile, 1) == split - 1;
             drain_sync();
             finish = *s_last != 0;
             if (finish) {
@@ -288,7 +292,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 for (int i = 0; i < NDIM; ++i) acc[i] = 0.f;
                 for (int sp = 0; sp < split; ++sp) {           // fixed order: deterministic sum
                     const float4* p = reinterpret_cast<const float4*>(
-                        scratch + ((size_t)(blockIdx.x * split + sp) * TC_ROWS + r) * NDIM);
+                        scratch + ((size_t)(wtile * split + sp) * TC_ROWS + r) * NDIM);
 #pragma unroll
                     for (int i = 0; i < NDIM; i += 4) {
                         const float4 t = __ldcg(p + i / 4);
@@ -298,12 +302,12 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             }
         }
         if (finish && o < n) {
-            float4* dst = reinterpret_cast<float4*>(out + (size_t)o * NDIM);
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)o * n_total + ntile * NDIM);
 #pragma unroll
             for (int i = 0; i < NDIM; i += 4) {
                 float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
                 if (bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + i));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + ntile * NDIM + i));
                     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                 }
                 if (act == 1) {
@@ -325,17 +329,17 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
 
 // Offsets of a tile are split over `split` CTAs when the level is too small to fill the GPU (two CTAs
 // are resident per SM): the largest split in 1..4 that keeps the whole grid in one wave.
-static inline int tc_split_for(int n_cap)
+static inline int tc_split_for(int n_cap, int ntiles)
 {
-    const int tiles = cdiv(n_cap, TC_ROWS);
+    const int tiles = cdiv(n_cap, TC_ROWS) * ntiles;
     const int split = (2 * 148) / tiles;
     return split < 1 ? 1 : (split > 4 ? 4 : split);
 }
 
 template <int KDIM, int NDIM>
 int launch_tc(const float* in, const int* nbr, int n_cap, const int* n_dev, int K, const float* bimg,
-              const float* bias, int act, float slope, float* out, void* workspace, size_t workspace_bytes,
-              cudaStream_t st)
+              const float* bias, int act, float slope, float* out, int n_total, void* workspace,
+              size_t workspace_bytes, cudaStream_t st)
 {
     using S = TcSmem<KDIM, NDIM>;
     static bool configured = false;
@@ -343,25 +347,32 @@ int launch_tc(const float* in, const int* nbr, int n_cap, const int* n_dev, int 
         RSLO_CHECK(cudaFuncSetAttribute(k_spconv_tc<KDIM, NDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         configured = true;
     }
-    const int tiles = cdiv(n_cap, TC_ROWS);
-    const int split = tc_split_for(n_cap);
+    const int tiles = cdiv(n_cap, TC_ROWS), ntiles = n_total / NDIM;
+    const int split = tc_split_for(n_cap, ntiles);
     float* scratch = nullptr;
     int* counter = nullptr;
     if (split > 1) {
         Workspace ws(workspace, workspace_bytes);
-        counter = ws.take<int>(tiles);
-        scratch = ws.take<float>((size_t)tiles * split * TC_ROWS * NDIM);
+        counter = ws.take<int>((size_t)tiles * ntiles);
+        scratch = ws.take<float>((size_t)tiles * ntiles * split * TC_ROWS * NDIM);
         if (!scratch) {
             set_last_error("rslo_spconv_tc_forward: workspace too small", cudaErrorMemoryAllocation);
             return (int)cudaErrorMemoryAllocation;
         }
-        RSLO_CHECK(cudaMemsetAsync(counter, 0, (size_t)tiles * sizeof(int), st));
+        RSLO_CHECK(cudaMemsetAsync(counter, 0, (size_t)tiles * ntiles * sizeof(int), st));
     }
     RSLO_COUNT();
-    k_spconv_tc<KDIM, NDIM><<<dim3(tiles, split), TC_THREADS, S::TOTAL, st>>>(in, nbr, n_cap, n_dev, K, bimg, bias, act,
-                                                                             slope, out, scratch, counter);
+    k_spconv_tc<KDIM, NDIM><<<dim3(tiles, split, ntiles), TC_THREADS, S::TOTAL, st>>>(
+        in, nbr, n_cap, n_dev, K, bimg, bias, act, slope, out, n_total, scratch, counter);
     RSLO_CHECK_LAUNCH("rslo_spconv_tc");
     return 0;
+}
+
+// output-channel tile of a layer: 64 where it divides, else 32
+static inline int tc_ntile(int ndim) { return ndim % 64 == 0 ? 64 : 32; }
+static inline bool tc_kdim_ok(int kdim)
+{
+    return kdim == 32 || kdim == 64 || kdim == 128 || kdim == 192 || kdim == 256 || kdim == 512;
 }
 
 }  // namespace
@@ -371,7 +382,8 @@ using namespace rslo;
 
 extern "C" int rslo_spconv_tc_supported(int Cin, int Cout, int K)
 {
-    return (Cin == 32 || Cin == 64) && (Cout == 32 || Cout == 64) && K >= 1 && K <= 27;
+    // both directions must be expressible: forward (kdim = Cin, ndim = Cout) and data gradient (swapped)
+    return tc_kdim_ok(Cin) && tc_kdim_ok(Cout) && K >= 1 && K <= 27;
 }
 
 extern "C" size_t rslo_spconv_tc_image_bytes(int K, int Cin, int Cout) { return (size_t)K * Cin * Cout * 8; }
@@ -384,18 +396,22 @@ extern "C" int rslo_spconv_tc_prepare(const float* weight, int K, int Cin, int C
         return (int)cudaErrorInvalidValue;
     }
     const int tot = K * Cin * Cout;
+    const int ndim = transpose ? Cin : Cout;
     RSLO_COUNT();
-    k_tc_prep<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, Cin, Cout, transpose, mirror, image);
+    k_tc_prep<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, Cin, Cout, transpose, mirror, tc_ntile(ndim),
+                                                               image);
     RSLO_CHECK_LAUNCH("rslo_spconv_tc_prepare");
     return 0;
 }
 
 extern "C" size_t rslo_spconv_tc_workspace_bytes(int n_out_cap, int ndim)
 {
-    const int tiles = cdiv(n_out_cap > 0 ? n_out_cap : 1, TC_ROWS);
-    const int split = tc_split_for(n_out_cap > 0 ? n_out_cap : 1);
+    const int n = n_out_cap > 0 ? n_out_cap : 1;
+    const int nt = tc_ntile(ndim), ntiles = ndim / nt;
+    const int tiles = cdiv(n, TC_ROWS) * ntiles;
+    const int split = tc_split_for(n, ntiles);
     if (split <= 1) return 256;
-    return ws_round((size_t)tiles * sizeof(int)) + ws_round((size_t)tiles * split * TC_ROWS * ndim * sizeof(float)) + 256;
+    return ws_round((size_t)tiles * sizeof(int)) + ws_round((size_t)tiles * split * TC_ROWS * nt * sizeof(float)) + 256;
 }
 
 extern "C" int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n_out_cap, const int32_t* n_out_dev,
@@ -405,18 +421,25 @@ extern "C" int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_out_cap <= 0) return 0;
-    if (K < 1 || K > 27) {
-        set_last_error("rslo_spconv_tc_forward: K must be in 1..27", cudaErrorInvalidValue);
+    if (K < 1 || K > 27 || !tc_kdim_ok(kdim) || !tc_kdim_ok(ndim)) {
+        set_last_error("rslo_spconv_tc_forward: unsupported (K, kdim, ndim)", cudaErrorInvalidValue);
         return (int)cudaErrorInvalidValue;
     }
-#define RSLO_TC_CASE(KD, ND)                                                                                      \
-    if (kdim == KD && ndim == ND)                                                                                 \
-        return launch_tc<KD, ND>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, workspace,       \
-                                 workspace_bytes, st);
-    RSLO_TC_CASE(64, 64)
-    RSLO_TC_CASE(64, 32)
-    RSLO_TC_CASE(32, 64)
-    RSLO_TC_CASE(32, 32)
+    const int nt = tc_ntile(ndim);
+#define RSLO_TC_CASE(KD)                                                                                          \
+    if (kdim == KD) {                                                                                             \
+        if (nt == 64)                                                                                             \
+            return launch_tc<KD, 64>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, ndim,       \
+                                     workspace, workspace_bytes, st);                                             \
+        return launch_tc<KD, 32>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, ndim, workspace, \
+                                 workspace_bytes, st);                                                            \
+    }
+    RSLO_TC_CASE(32)
+    RSLO_TC_CASE(64)
+    RSLO_TC_CASE(128)
+    RSLO_TC_CASE(192)
+    RSLO_TC_CASE(256)
+    RSLO_TC_CASE(512)
 #undef RSLO_TC_CASE
     set_last_error("rslo_spconv_tc_forward: unsupported (kdim, ndim)", cudaErrorInvalidValue);
     return (int)cudaErrorInvalidValue;

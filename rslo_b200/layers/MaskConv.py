@@ -2,6 +2,8 @@
 import torch
 from torch import nn
 
+from .conv2d_tc import Conv2dTC
+
 
 class MaskConv(nn.Module):
     """conv(bias=False) on the features in parallel with a max-pool of the occupancy mask; returns
@@ -18,7 +20,7 @@ class MaskConv(nn.Module):
         assert max_pool_mask, "only the max-pool mask variant is used by the shipped configs"
         self.out_channels = out_channels
         self.use_bias = bias
-        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, bias=False,
+        self.conv1 = Conv2dTC(in_channels, out_channels, kernel_size=kernel_size, stride=stride, bias=False,
                                padding=padding, groups=groups)
         self.max_pool_mask = max_pool_mask
         self.propagate_mask = propagate_mask

@@ -20,6 +20,7 @@ from torch.nn import functional as F
 from ..data.dataset import cell_anchors, from_pointwise_local_transformation_tch
 from ..layers.common import ParameterLayer
 from ..layers.confidence import ConfidenceModule
+from ..layers.conv2d_tc import Conv2dTC
 from ..layers.MaskConv import MaskConv
 from ..layers.SparseConv import SPC_BN2d, SPC_ReLU, SPC_SyncBN2d
 from ..torchplus import Empty, change_default_args
@@ -77,9 +78,9 @@ class BasicBlock(nn.Module):
 
 
 def _conf_stack(cin, BN, ReLU):
-    return nn.Sequential(nn.Conv2d(cin, 64, kernel_size=3, padding=1), BN(64), ReLU(),
-                         nn.Conv2d(64, 32, kernel_size=3, padding=1), BN(32), ReLU(),
-                         nn.Conv2d(32, 1, kernel_size=1))
+    return nn.Sequential(Conv2dTC(cin, 64, kernel_size=3, padding=1), BN(64), ReLU(),
+                         Conv2dTC(64, 32, kernel_size=3, padding=1), BN(32), ReLU(),
+                         Conv2dTC(32, 1, kernel_size=1))
 
 
 class _FlatHead(nn.Module):
@@ -138,7 +139,7 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
         bn_cls = SPC_SyncBN2d if (bn_type == "SyncBN" or sync_bn) else SPC_BN2d
         self.BatchNorm2d = change_default_args(eps=1e-3, momentum=0.01)(bn_cls)
         self.ReLU = SPC_ReLU
-        Conv2d = change_default_args(bias=True)(nn.Conv2d)
+        Conv2d = change_default_args(bias=True)(Conv2dTC)
         BN, ReLU = self.BatchNorm2d, self.ReLU
 
         in_filters = [num_input_features, *num_filters[:-1]]
@@ -152,13 +153,13 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
         for i in range(len(num_upsample_filters)):
             cin = num_filters[-1] * 2 if i == 0 else num_upsample_filters[i - 1] + num_filters[-(i + 1)]
             deblocks.append(nn.Sequential(nn.Upsample(scale_factor=upsample_strides[i]),
-                                          nn.Conv2d(cin, num_upsample_filters[i], kernel_size=3, stride=1, padding=1),
+                                          Conv2dTC(cin, num_upsample_filters[i], kernel_size=3, stride=1, padding=1),
                                           BN(num_upsample_filters[i]), ReLU()))
             if self.pred_pyramid_motion:
                 c = num_upsample_filters[i]
-                py_blocks.append(nn.Sequential(nn.Conv2d(c, c // 2, kernel_size=3, stride=1, padding=1), BN(c // 2), ReLU(),
-                                               nn.Conv2d(c // 2, 64, kernel_size=3, stride=1, padding=1), BN(64), ReLU(),
-                                               nn.Conv2d(64, 7, 1, stride=1)))
+                py_blocks.append(nn.Sequential(Conv2dTC(c, c // 2, kernel_size=3, stride=1, padding=1), BN(c // 2), ReLU(),
+                                               Conv2dTC(c // 2, 64, kernel_size=3, stride=1, padding=1), BN(64), ReLU(),
+                                               Conv2dTC(64, 7, 1, stride=1)))
         if self.pred_pyramid_motion:
             self.mask_gen_pools = nn.ModuleList([nn.MaxPool2d(kernel_size=3, stride=s, padding=1) for s in upsample_strides])
         self.blocks = nn.ModuleList(blocks)
@@ -166,9 +167,9 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
         self.skip_blocks = nn.ModuleList(skip_blocks)
         self.pyramid_motion_blocks = nn.ModuleList(py_blocks)
         c_last = num_upsample_filters[-1]
-        self.tq_map_conv = nn.Sequential(nn.Conv2d(c_last, 64, kernel_size=3, padding=1), BN(64), ReLU(),
-                                         nn.Conv2d(64, 32, kernel_size=3, padding=1), BN(32), ReLU(),
-                                         nn.Conv2d(32, 7, kernel_size=1))
+        self.tq_map_conv = nn.Sequential(Conv2dTC(c_last, 64, kernel_size=3, padding=1), BN(64), ReLU(),
+                                         Conv2dTC(64, 32, kernel_size=3, padding=1), BN(32), ReLU(),
+                                         Conv2dTC(32, 7, kernel_size=1))
         self.q_map_conf = ConfidenceModule(_conf_stack(c_last, BN, ReLU), conf_type=conf_type)
         self.t_map_conf = ConfidenceModule(_conf_stack(c_last, BN, ReLU), conf_type=conf_type)
         self.pool = nn.AdaptiveAvgPool2d((pooling_size, pooling_size)) if pooling_type == "avg_pool" \

@@ -391,3 +391,38 @@ def test_stress_grid_voxelize_and_rulebook_bit_exact(K):
     d1, i1 = K.nn_exact(q, t)
     d2, i2 = K.nn_exact(q, t, brute=True)
     assert torch.equal(i1, i2) and torch.equal(d1, d2)
+
+
+@pytest.mark.parametrize("cin,cout,h,w,ks,st,B", [(256, 128, 24, 44, 3, 2, 1), (128, 128, 24, 22, 3, 1, 2),
+                                                  (512, 128, 12, 22, 3, 1, 1), (192, 64, 48, 44, 3, 1, 1),
+                                                  (64, 32, 48, 88, 3, 1, 1), (256, 128, 24, 44, 1, 2, 1),
+                                                  (256, 256, 12, 22, 3, 1, 3)])
+def test_conv2d_tensor_core_matches_fp64(cuda, cin, cout, h, w, ks, st, B):
+    """Head convolution on the tensor-core gather-GEMM (channels_last rows + static neighbour table):
+    forward, data gradient (TC) and weight gradient (cuDNN) against float64 autograd."""
+    from rslo_b200.layers import conv2d_tc
+    from rslo_b200.layers.conv2d_tc import Conv2dTC
+    monkey = conv2d_tc.USE_TC
+    conv2d_tc.USE_TC = True
+    g = torch.Generator().manual_seed(cin + cout + h)
+    conv = Conv2dTC(cin, cout, ks, stride=st, padding=ks // 2, bias=True).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (cin * ks * ks)) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    x = torch.randn(B, cin, h, w, generator=g).cuda().requires_grad_(True)
+    y = conv(x)
+    go = torch.randn(y.shape, generator=g).cuda()
+    y.backward(go)
+    xd = x.detach().double().requires_grad_(True)
+    wd = conv.weight.detach().double().requires_grad_(True)
+    bd = conv.bias.detach().double().requires_grad_(True)
+    yd = torch.nn.functional.conv2d(xd, wd, bd, st, ks // 2)
+    yd.backward(go.double())
+    def rel(a, b):
+        return float((a.double() - b).abs().max() / b.abs().max())
+    assert y.shape == yd.shape
+    assert rel(y, yd) < 5e-6
+    assert rel(x.grad, xd.grad) < 5e-6
+    assert rel(conv.weight.grad, wd.grad) < 1e-4          # cuDNN FP32 weight gradient
+    assert rel(conv.bias.grad, bd.grad) < 1e-5
+    conv2d_tc.USE_TC = monkey
