@@ -24,6 +24,10 @@
 // Small levels are split over gridDim.y CTAs per tile (disjoint offsets) so all 148 SMs have work.
 #include "tc_common.cuh"
 
+#ifndef TC_DIAG
+#define TC_DIAG 0      // 1..5: timing-only diagnostics (scripts/diag_tc.sh); results are wrong when non-zero
+#endif
+
 namespace rslo {
 namespace {
 using namespace tc;
@@ -178,7 +182,9 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 const int r = warp * 32 + j * ROWS_PER_LD + sub;
                 const int src = s_nbr[r * K + k];
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#if TC_DIAG != 3
                 if (src >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM + h * TC_KS) + c);
+#endif
             }
         };
         // split to TF32 {hi, lo} and store into stage s in the UMMA layout; then publish the stage
@@ -186,15 +192,23 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             const int s = st % TC_STAGES;
             mbar_wait(empty_bar + s, ((st / TC_STAGES) & 1) ^ 1);
             const uint32_t stage = smem_base + s * S::STAGE_BYTES;
+#if TC_DIAG == 1
+            if (tid == 0 && st < TC_STAGES) {
+#else
             if (tid == 0) {
+#endif
                 mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
                 bulk_copy_g2s(smem + s * S::STAGE_BYTES + 2 * S::A_BYTES,
                               (const char*)bimg + ((size_t)k * NSUB + h) * (2 * S::B_BYTES), 2 * S::B_BYTES, full_bar + s);
             }
 #pragma unroll
             for (int j = 0; j < NLD; ++j) {
+#if TC_DIAG == 2
+                const float4 hh = v[j], ll = v[j];
+#else
                 const float4 hh = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
                 const float4 ll = make_float4(v[j].x - hh.x, v[j].y - hh.y, v[j].z - hh.z, v[j].w - hh.w);
+#endif
                 sts128(stage + soff[j], hh);
                 sts128(stage + S::A_BYTES + soff[j], ll);
             }
@@ -239,7 +253,9 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                         const uint32_t b = part == 1 ? b_lo : b_hi;
 #pragma unroll
                         for (int kk = 0; kk < TC_KS / 8; ++kk) {
+#if TC_DIAG != 4
                             umma_tf32(d, umma_desc_k_sw128(a + kk * 32), umma_desc_k_sw128(b + kk * 32), idesc, acc);
+#endif
                             acc = 1;
                         }
                     }
@@ -266,6 +282,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             mbar_wait(tfull_bar + buf, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NDIM;
+#if TC_DIAG != 5
 #pragma unroll
             for (int cb = 0; cb < NDIM; cb += 16) {
                 float v[16];
@@ -273,6 +290,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
 #pragma unroll
                 for (int i = 0; i < 16; ++i) acc[cb + i] += v[i];
             }
+#endif
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty_bar + buf);
         }
