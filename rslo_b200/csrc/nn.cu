@@ -18,7 +18,7 @@
 namespace rslo {
 namespace {
 
-constexpr int NN_MAX_RING = 12;
+constexpr int NN_MAX_RING = 40;
 constexpr int NN_BRUTE_BELOW = 2048;  // m below which the grid is not worth building
 
 struct NNGrid {
