@@ -121,19 +121,37 @@ class _DenseFramesFn(torch.autograd.Function):
         return grad, None
 
 
+class _ImageCache:
+    """Pre-swizzled split-TF32 weight images of one layer (csrc/spconv_tc.cu), rebuilt only when the weight
+    changes (tensor version counter): the frames / pairs of a step share them."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, weight, transpose, mirror):
+        key = (bool(transpose), bool(mirror))
+        ver = (weight._version, weight.data_ptr())
+        hit = self._c.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, K.spconv_tc_prepare(weight.detach(), transpose=transpose, mirror=mirror))
+            self._c[key] = hit
+        return hit[1]
+
+
 class _SpConvFn(torch.autograd.Function):
     """out = act(bias + sum_k in[nbr[:,k]] @ W[k]); LeakyReLU fused (slope > 0 keeps it invertible
     from the saved output's sign)."""
 
     @staticmethod
-    def forward(ctx, feat, weight, bias, entry, inverse, act, slope):
+    def forward(ctx, feat, weight, bias, entry, inverse, act, slope, images=None):
         nbr = entry.nbr_t if inverse else entry.nbr
         n_out = entry.n_in if inverse else entry.n_out
         feat = feat.contiguous()
         Kk, Cin, Cout = weight.shape
         ctx.tc = USE_TC and K.spconv_tc_supported(Cin, Cout, Kk)
         if ctx.tc:
-            img = K.spconv_tc_prepare(weight)
+            ctx.images = images if images is not None else _ImageCache()
+            img = ctx.images.get(weight, False, False)
             out = K.spconv_tc_forward(feat, nbr, n_out, img, Cin, Cout, bias, act=act, slope=slope)
         else:
             out = K.spconv_forward(feat, nbr, n_out, weight, bias, act=act, slope=slope)
@@ -157,7 +175,7 @@ class _SpConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if ctx.tc:
                 Kk, Cin, Cout = weight.shape
-                img_t = K.spconv_tc_prepare(weight, transpose=True, mirror=e.mirror)
+                img_t = ctx.images.get(weight, True, e.mirror)
                 gi = K.spconv_tc_forward(g, nbr_t, n_in, img_t, Cout, Cin)
             else:
                 gi = K.spconv_backward_data(g, nbr_t, n_in, weight, e.mirror)
@@ -166,7 +184,7 @@ class _SpConvFn(torch.autograd.Function):
                 gw = K.spconv_tc_backward_weight(feat, g, nbr, n_out, weight.shape)
             else:
                 gw, _ = K.spconv_backward_weight(feat, g, nbr, n_out, weight.shape, need_bias=False)
-        return gi, gw, gb_fused, None, None, None, None
+        return gi, gw, gb_fused, None, None, None, None, None
 
 
 def _triple(v):
@@ -182,6 +200,7 @@ class SparseConvolution(nn.Module):
         self.subm, self.inverse, self.indice_key = subm, inverse, indice_key
         self.weight = nn.Parameter(torch.empty(*self.kernel_size, in_channels, out_channels))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self._images = _ImageCache()
         self.fused_act = 0          # set by SparseSequential when a LeakyReLU follows
         self.fused_slope = 0.01
         self.reset_parameters()
@@ -216,7 +235,8 @@ class SparseConvolution(nn.Module):
     def forward(self, x):
         e = self._entry(x)
         w = self.weight.view(-1, self.in_channels, self.out_channels)
-        out = _SpConvFn.apply(x.features, w, self.bias, e, self.inverse, self.fused_act, self.fused_slope)
+        out = _SpConvFn.apply(x.features, w, self.bias, e, self.inverse, self.fused_act, self.fused_slope,
+                              self._images)
         if self.inverse:
             # lands on the INPUT site set of the keyed conv
             return x.shadow(out, e.in_indices, e.in_shape, e.in_table, e.n_in, seg=e.seg_in,
