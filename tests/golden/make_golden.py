@@ -38,6 +38,7 @@ CASES = {
     "small_train_warm": (1, 16, 600, 2, 100, 12),       # step <= 1500: identity pose, 5 ICP iterations
     "small_train_t3": (2, 16, 400, 3, 2000, 13),        # seq_length 3 -> 3 pairs (train prototxt)
     "full_eval": (0, 64, 1875, 2, 2000, 11),            # BASELINE config C1/C2: 120k-pt pair
+    "full_train": (3, 64, 1875, 2, 2000, 14),           # BASELINE config C3: 120k-pt pair, fwd + bwd
 }
 
 

@@ -45,7 +45,7 @@ def test_oracle_eval_matches_reference_golden(our_sd):
     np.testing.assert_allclose(out["cov"][0][::97].numpy(), g["cov0_sample"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["small_train", "small_train_warm", "small_train_t3"])
+@pytest.mark.parametrize("name", ["small_train", "small_train_warm", "small_train_t3", "full_train"])
 def test_oracle_train_matches_reference_golden(our_sd, name):
     g, sd, frames, step = _case(our_sd, name)
     out = onet.pair_forward(sd, frames, training=True, step=step, grads_for=mg.GRAD_KEYS)

@@ -58,7 +58,7 @@ def test_eval_matches_reference_golden(net, name):
     assert _rel(out["tq_map_g"].abs().sum(dim=(1, 2, 3)).cpu().numpy(), g["tq_map_g_abs_sum"]) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["small_train", "small_train_warm", "small_train_t3"])
+@pytest.mark.parametrize("name", ["small_train", "small_train_warm", "small_train_t3", "full_train"])
 def test_train_matches_reference_golden(net, name):
     net, vg = net
     g, frames, _ = _prep(net, name)
