@@ -1,6 +1,5 @@
 """ctypes bindings of oracle/c/oracle.c (numpy in, numpy out).  TEST INFRASTRUCTURE ONLY."""
 import ctypes as C
-import os
 
 import numpy as np
 

@@ -9,12 +9,10 @@ csrc/cov_residual.cu, the ICP alignment from csrc/kabsch.cu.
 """
 import torch
 from torch import nn
-from torch.nn import functional as F
 
 from .. import kernels as K
 from ..layers.svd import SVDHead
 from ..thirdparty.chamfer_distance.chamfer_distance import OneDirectionChamferDistanceWithIdx
-from ..utils import pose_utils
 
 
 class Loss(nn.Module):

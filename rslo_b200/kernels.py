@@ -9,7 +9,6 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
 from ._lib import check, lib, ptr, stream, workspace
 
 LAUNCHES = {"calls": 0}

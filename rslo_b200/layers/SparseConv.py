@@ -1,7 +1,6 @@
 """Tuple-aware normalisation / activation layers (`rslo/layers/SparseConv.py:96-132` and the
 SPC_ReLU / SPC_LeakyReLU / SPC_BN2d classes further down that file): they accept either a tensor or
 ``[tensor, mask]`` and pass the mask through."""
-import torch
 from torch import nn
 
 

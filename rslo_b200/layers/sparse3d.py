@@ -9,7 +9,6 @@ by csrc/rulebook.cu; there is no PyTorch or CPU fallback.
 import math
 import os
 
-import numpy as np
 import torch
 from torch import nn
 

@@ -12,12 +12,11 @@ The 2-D convolutions are dense contractions and run through cuDNN in FP32.
 """
 import os
 
-import numpy as np
 import torch
 from torch import nn
 from torch.nn import functional as F
 
-from ..data.dataset import cell_anchors, from_pointwise_local_transformation_tch
+from ..data.dataset import from_pointwise_local_transformation_tch
 from ..layers.common import ParameterLayer
 from ..layers.confidence import ConfidenceModule
 from ..layers.conv2d_tc import Conv2dTC

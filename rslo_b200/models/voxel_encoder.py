@@ -1,5 +1,4 @@
 """Voxel feature extractors (registry surface of `rslo/models/voxel_encoder.py:11-26`)."""
-import torch
 from torch import nn
 
 from .. import kernels as K

@@ -1,5 +1,5 @@
 """Time the tensor-core sparse-conv kernel alone on a realistic level (two frames' 64-channel level 2)."""
-import os, sys, torch, numpy as np
+import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rslo_b200 import kernels as K
 from rslo_b200.data import synthetic

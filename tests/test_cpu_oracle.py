@@ -11,7 +11,6 @@ import torch
 from oracle import native as onat
 from oracle import net as onet
 from oracle import quat, ref_shim
-from oracle import sparse as osp
 from rslo_b200.data import synthetic
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
