@@ -211,7 +211,7 @@ def main():
     import torch
     import torch.distributed as dist
     import rslo_b200
-    from oracle import net as onet            # fill_weights only (deterministic weights shared with the oracle)
+    from rslo_b200.utils.weights import deterministic_fill
     from rslo_b200 import kernels as K
     from rslo_b200.utils.distributed import FlatGradAllReducer, init_from_env
 
@@ -223,7 +223,7 @@ def main():
     ppg = cfg["pairs_per_gpu"]
 
     net, vg = rslo_b200.build_network(cfg.get("config_path"), testing=False, seed=7)
-    onet.fill_weights(net, WEIGHT_SEED)
+    deterministic_fill(net, WEIGHT_SEED)
     net = net.to(dev)
     net.global_step.fill_(STEP_AFTER_WARMUP)
     net._step_host = None

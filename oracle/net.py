@@ -11,7 +11,6 @@ golden fixtures under tests/golden/ (made by tests/golden/make_golden.py from th
 The head / loss / tq-map rows are therefore pinned to reference code; the voxeliser, rulebook and
 sparse-conv rows restate the un-vendored spconv_plus fork => parity unpinned for those.
 """
-import hashlib
 import math
 
 import numpy as np
@@ -26,50 +25,8 @@ SPARSE_SHAPE = [41, 768, 1408]
 BN_EPS_HEAD, BN_MOM_HEAD = 1e-3, 0.01          # odom_pred_base.py:140-141
 
 
-# ------------------------------------------------------------------------------------------------
-# deterministic weights: the same values for the reference net, the oracle and the CUDA path,
-# independent of module construction order (which consumes the global RNG differently per build)
-# ------------------------------------------------------------------------------------------------
-def fill_weights(target, seed=11):
-    """Fill a module's (or dict's) tensors in place from a per-key seeded generator.
-    Conv/linear weights ~ N(0, gain/fan_in); BN weight ~ 1+-0.1, bias small, running stats near
-    (0,1); loss alphas and integer buffers are left untouched."""
-    sd = target.state_dict() if hasattr(target, "state_dict") else target
-    with torch.no_grad():
-        for key in sorted(sd.keys()):
-            t = sd[key]
-            if not t.is_floating_point() or key.endswith("alpha") or key.endswith("reflect") or \
-                    "dynamic_sigma" in key:
-                continue
-            h = int(hashlib.sha256(f"{seed}:{key}".encode()).hexdigest()[:8], 16)
-            g = torch.Generator().manual_seed(h)
-            shape = tuple(t.shape)
-            leaf = key.rsplit(".", 1)[-1]
-            if leaf == "running_mean":
-                v = 0.05 * torch.randn(shape, generator=g)
-            elif leaf == "running_var":
-                v = 1.0 + 0.2 * torch.rand(shape, generator=g)
-            elif leaf == "bias" and shape == (7,) and ("tq_map_conv" in key or "pyramid_motion" in key):
-                # (t, q) regressors: keep the predicted pose near a plausible inter-frame motion
-                v = torch.tensor([0.6, 0.02, 0.0, 1.0, 0.003, 0.003, 0.008]) + 0.002 * torch.randn(shape, generator=g)
-            elif leaf == "bias":
-                v = 0.05 * torch.randn(shape, generator=g)
-            elif leaf == "weight" and t.dim() == 1:
-                v = 1.0 + 0.1 * torch.randn(shape, generator=g)
-                if ".bn2." in key:          # keep the residual branches small: no blow-up in eval mode
-                    v = 0.3 * v
-            elif leaf == "weight" and t.dim() == 5:          # sparse conv [kD,kH,kW,Cin,Cout]
-                fan_in = shape[0] * shape[1] * shape[2] * shape[3]
-                v = torch.randn(shape, generator=g) * math.sqrt(6.0 / fan_in)
-            elif leaf == "weight":                           # conv2d [Cout,Cin,kh,kw] / linear
-                fan_in = int(np.prod(shape[1:]))
-                v = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
-                if shape[0] == 7 and ("tq_map_conv" in key or "pyramid_motion" in key):
-                    v = v * 0.003
-            else:
-                continue
-            t.copy_(v.to(t.dtype))
-    return target
+# deterministic weights shared by every implementation (reference net, oracle, CUDA path)
+from rslo_b200.utils.weights import deterministic_fill as fill_weights  # noqa: E402,F401
 
 
 # ------------------------------------------------------------------------------------------------
