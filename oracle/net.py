@@ -11,7 +11,6 @@ golden fixtures under tests/golden/ (made by tests/golden/make_golden.py from th
 The head / loss / tq-map rows are therefore pinned to reference code; the voxeliser, rulebook and
 sparse-conv rows restate the un-vendored spconv_plus fork => parity unpinned for those.
 """
-import math
 
 import numpy as np
 import torch
