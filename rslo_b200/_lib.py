@@ -99,10 +99,11 @@ _WS = {}
 
 
 def workspace(nbytes, slot="default"):
-    """Growable per-(device, slot) scratch buffer; stream-ordered reuse on the current stream."""
+    """Growable per-(device, stream, slot) scratch buffer: reuse is ordered by the stream it belongs to, so
+    work on different streams (preparation stream, concurrent examples) never shares scratch memory."""
     import torch
     dev = torch.cuda.current_device()
-    key = (dev, slot)
+    key = (dev, torch.cuda.current_stream().cuda_stream, slot)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=f"cuda:{dev}")

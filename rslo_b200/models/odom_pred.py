@@ -235,7 +235,9 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
     use_cuda_graph = os.environ.get("RSLO_CUDA_GRAPHS", "1") != "0"
 
     def _forward_graphed(self, xs):
-        key = (len(xs), self.training, tuple(x.requires_grad for x in xs), tuple(xs[0].shape), xs[0].device.index)
+        # one captured graph per stream: replays on different streams must not share static buffers
+        key = (len(xs), self.training, tuple(x.requires_grad for x in xs), tuple(xs[0].shape), xs[0].device.index,
+               torch.cuda.current_stream().cuda_stream)
         cache = self.__dict__.setdefault("_graphed", {})
         g = cache.get(key)
         if g is None:

@@ -296,6 +296,7 @@ class UnVoxelOdomNetICP3(nn.Module):
         if "_prepared" in example:
             prep = example["_prepared"]
             torch.cuda.current_stream().wait_event(prep["event"])
+            _record_stream_tree(prep["frames"], torch.cuda.current_stream())
             example = dict(example)
             example["_prepared_frames"] = prep["frames"]
             voxels, coors = prep["frames"]["features"], prep["frames"]["coors"]
@@ -528,7 +529,8 @@ class UnVoxelOdomNetICP3(nn.Module):
             return self._loss_tail_eager(T_pred, q_pred, flat, res_r, res_t, identity_pose)
         args = (T_pred, q_pred, *flat, res_r, res_t)
         key = (identity_pose, self._translation_loss._loss_weight, self._rotation_loss._loss_weight,
-               tuple((tuple(a.shape), a.requires_grad) for a in args), T_pred.device.index)
+               tuple((tuple(a.shape), a.requires_grad) for a in args), T_pred.device.index,
+               torch.cuda.current_stream().cuda_stream)
         cache = self.__dict__.setdefault("_graphed_tail", {})
         g = cache.get(key)
         if g is None:

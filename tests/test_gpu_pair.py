@@ -162,3 +162,4 @@ def test_prepared_example_matches_direct_call(net):
         c = net(ex2)
     for k in ("translation_preds", "rotation_preds", "tq_map_g"):
         assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+
