@@ -250,9 +250,13 @@ def main():
             h2d_bytes[0] += a.numel() * 4 + b.numel() * 4
         return net.prepare({"points": [a, b], "host_outputs": False})
 
+    image_caches = [m._images for m in net.modules() if hasattr(m, "_images")]
+
     def step(i, from_host):
         if train:
             reducer.zero_()
+            for c in image_caches:          # a real training step changes the weights: rebuild the split-TF32
+                c._c.clear()                # weight images once per step, as an optimizer step would force
         outs = []
         for j in range(ppg):
             idx = i * ppg + j
