@@ -137,15 +137,20 @@ __global__ void k_vox_filter(const int* __restrict__ n_cells_dev, const int* __r
 
 constexpr int MAXP_LIMIT = 32;
 
-__global__ void k_vox_gather(const float* __restrict__ pts, int F, const int* __restrict__ n_cells_dev,
-                             const int* __restrict__ first, const uint2* __restrict__ ptbits,
-                             const int* __restrict__ offsets, const int* __restrict__ cnt,
-                             const int* __restrict__ seg, const unsigned* __restrict__ keys,
-                             int max_points, int max_voxels, int gx, int gy,
-                             const int* __restrict__ keep, const int* __restrict__ newid, int batch_idx,
-                             float* __restrict__ voxels, int* __restrict__ coors, int coor_stride,
-                             int* __restrict__ num_points, float* __restrict__ mean,
-                             int* __restrict__ perm)
+// One thread per occupied cell.  The `max_points` smallest point indices of the cell are kept in a
+// register-resident sorted list (static-index compare-exchange insertion: MAXP is a compile-time bound, so
+// nothing spills to local memory), then the selected rows are read once for `voxels` and/or the fused mean.
+template <int MAXP>
+__global__ void __launch_bounds__(128)
+k_vox_gather(const float* __restrict__ pts, int F, const int* __restrict__ n_cells_dev,
+             const int* __restrict__ first, const uint2* __restrict__ ptbits,
+             const int* __restrict__ offsets, const int* __restrict__ cnt,
+             const int* __restrict__ seg, const unsigned* __restrict__ keys,
+             int max_points, int max_voxels, int gx, int gy,
+             const int* __restrict__ keep, const int* __restrict__ newid, int batch_idx,
+             float* __restrict__ voxels, int* __restrict__ coors, int coor_stride,
+             int* __restrict__ num_points, float* __restrict__ mean,
+             int* __restrict__ perm)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= *n_cells_dev) return;
@@ -157,44 +162,48 @@ __global__ void k_vox_gather(const float* __restrict__ pts, int F, const int* __
     if (perm) perm[r] = row;
     if (row < 0) return;
 
-    // the max_points smallest point indices of this cell, ascending
-    int sel[MAXP_LIMIT];
-    int c = cnt[r];
+    int sel[MAXP];
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) sel[q] = INT_MAX;
+    const int c = cnt[r];
     const int* s = seg + offsets[r];
-    int m = 0;
     for (int j = 0; j < c; ++j) {
-        int v = s[j];
-        if (m < max_points) {
-            int q = m++;
-            while (q > 0 && sel[q - 1] > v) { sel[q] = sel[q - 1]; --q; }
-            sel[q] = v;
-        } else if (v < sel[m - 1]) {
-            int q = m - 1;
-            while (q > 0 && sel[q - 1] > v) { sel[q] = sel[q - 1]; --q; }
-            sel[q] = v;
+        int v = __ldg(s + j);
+#pragma unroll
+        for (int q = 0; q < MAXP; ++q) {                 // keeps sel[] ascending; v carries the displaced value
+            const int lo = min(v, sel[q]);
+            v = max(v, sel[q]);
+            sel[q] = lo;
         }
     }
+    const int m = min(c, max_points);
     unsigned key = keys[f];
     int x = key % gx, y = (key / gx) % gy, z = key / (gx * gy);
     int* co = coors + (size_t)row * coor_stride;
     if (coor_stride == 4) { co[0] = batch_idx; ++co; }
     co[0] = z; co[1] = y; co[2] = x;
     num_points[row] = m;
-    if (voxels) {
-        float* vo = voxels + (size_t)row * max_points * F;
-        for (int q = 0; q < max_points; ++q)
-            for (int a = 0; a < F; ++a)
-                vo[q * F + a] = q < m ? pts[(size_t)sel[q] * F + a] : 0.f;
+    float acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    float* vo = voxels ? voxels + (size_t)row * max_points * F : nullptr;
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) {
+        if (q < max_points) {
+            if (q < m) {
+                const float* p = pts + (size_t)sel[q] * F;
+                if (vo)
+                    for (int a = 0; a < F; ++a) vo[q * F + a] = p[a];
+                if (mean) {
+#pragma unroll
+                    for (int a = 0; a < 7; ++a) acc[a] += p[a];
+                }
+            } else if (vo) {
+                for (int a = 0; a < F; ++a) vo[q * F + a] = 0.f;
+            }
+        }
     }
     if (mean) {
         // SimpleVoxel_XYZINormalC (voxel_encoder.py:272-280): mean of the stored points, then the
         // normal (cols 4:7) renormalised with eps 1e-12.
-        float acc[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int q = 0; q < m; ++q) {
-            const float* p = pts + (size_t)sel[q] * F;
-#pragma unroll
-            for (int a = 0; a < 7; ++a) acc[a] += p[a];
-        }
         float fm = (float)m;
 #pragma unroll
         for (int a = 0; a < 7; ++a) acc[a] = acc[a] / fm;
@@ -332,10 +341,16 @@ extern "C" int rslo_voxelize(const float* points, int P, int F, const float* vs,
         if (rc) return rc;
     }
     RSLO_COUNT();
-    k_vox_gather<<<cdiv(P, 128), 128, 0, st>>>(points, F, counters + 0, first, ptbits, offsets, cnt, seg,
-                                              keys, max_points, max_voxels, gx, gy, keep, newid,
-                                              batch_idx, voxels, coors, coor_stride, num_points, mean,
-                                              perm);
+    if (max_points <= 10)
+        k_vox_gather<10><<<cdiv(P, 128), 128, 0, st>>>(points, F, counters + 0, first, ptbits, offsets, cnt, seg,
+                                                      keys, max_points, max_voxels, gx, gy, keep, newid,
+                                                      batch_idx, voxels, coors, coor_stride, num_points, mean,
+                                                      perm);
+    else
+        k_vox_gather<MAXP_LIMIT><<<cdiv(P, 128), 128, 0, st>>>(points, F, counters + 0, first, ptbits, offsets, cnt,
+                                                              seg, keys, max_points, max_voxels, gx, gy, keep,
+                                                              newid, batch_idx, voxels, coors, coor_stride,
+                                                              num_points, mean, perm);
     RSLO_COUNT();
     k_vox_count<<<1, 32, 0, st>>>(counters + 0, max_voxels, filter ? counters + 2 : nullptr,
                                   n_voxels_dev);
