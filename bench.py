@@ -368,7 +368,12 @@ def main():
                     "frac": achieved / peak, "traffic": measured_traffic(nm), "peak_source": peak_src,
                     "launches_per_step": a[0] / nprof, "avg_launch_ms": a[1] / a[0],
                     "algorithmic_bytes_per_launch": a[2] / a[0], "gflops_per_launch": a[3] / a[0] / 1e9,
-                    "share_of_step": a[1] / nprof / step_ms}
+                    "share_of_step": a[1] / nprof / step_ms,
+                    # the same launches seen as a contraction: useful FLOP/s (2*R*Cin*Cout); the split-TF32 scheme
+                    # executes 3x that on the tensor pipe (ncu: 32 % tensor-pipe active, smem-bandwidth bound)
+                    "useful_tflops": (a[3] / (a[1] * 1e-3) / 1e12) if a[1] > 0 else None,
+                    "note": "dominant OWN kernel by summed CUDA-event time; the cuDNN FP32 head is the larger share "
+                            "of the step (profiles/r01_launches_bench.md)"}
     if world > 1:
         dist.barrier()
 
