@@ -197,3 +197,22 @@ def test_oracle_matches_reference_live():
     np.testing.assert_allclose(out["loss"].reshape(-1), ret["loss"].detach().numpy().reshape(-1), rtol=1e-5)
     np.testing.assert_allclose(out["pose"], torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1).numpy(),
                                rtol=1e-5, atol=1e-6)
+
+
+def test_quaternion_conversions_vs_scipy():
+    """kornia 0.4.0 is not vendored (parity unpinned): cross-check the restatement against an independent
+    implementation (scipy Rotation, same x,y,z,w convention), incl. the four branches of the matrix->quaternion
+    conversion."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=(256, 4))
+    q[:8] = np.array([[1, 0, 0, 1e-4], [0, 1, 0, 1e-4], [0, 0, 1, 1e-4], [0, 0, 0, 1],
+                      [0.7, 0.7, 0, 0.1], [0, 0.7, 0.7, 0.1], [0.7, 0, 0.7, 0.1], [1, 1, 1, 1]])   # all trace branches
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    R_ref = Rotation.from_quat(q).as_matrix()
+    R = quat.quaternion_to_rotation_matrix(torch.from_numpy(q)).numpy()
+    np.testing.assert_allclose(R, R_ref, atol=1e-12)
+    q_back = quat.rotation_matrix_to_quaternion(torch.from_numpy(R_ref)).numpy()
+    q_ref = Rotation.from_matrix(R_ref).as_quat()
+    sgn = np.sign(np.sum(q_back * q_ref, axis=1, keepdims=True))
+    np.testing.assert_allclose(q_back * sgn, q_ref, atol=1e-6)
