@@ -151,6 +151,7 @@ int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n_out_cap, c
 
 /* Weight gradient on the tensor cores (csrc/spconv_tc_wgrad.cu): dW[k] = sum_o in[nbr[o,k],:]^T (x) g[o,:]
  * as MN-major tcgen05 MMAs with the offsets stacked along M; grad_weight [K,Cin,Cout] is zeroed inside. */
+int rslo_spconv_tc_wgrad_supported(int Cin, int Cout);
 int rslo_spconv_tc_backward_weight(const float* in, const float* grad_out, const int32_t* nbr, int n_out_cap,
                                    const int32_t* n_out_dev, int K, int Cin, int Cout, float* grad_weight,
                                    rslo_stream_t stream);

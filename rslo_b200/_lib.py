@@ -46,6 +46,7 @@ SIGNATURES = {
     "rslo_spconv_tc_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rslo_spconv_tc_workspace_bytes": (_sz, [_i, _i]),
     "rslo_spconv_tc_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _sz, _vp]),
+    "rslo_spconv_tc_wgrad_supported": (_i, [_i, _i]),
     "rslo_spconv_tc_backward_weight": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rslo_dense_from_sites": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rslo_kabsch_workspace_bytes": (_sz, []),

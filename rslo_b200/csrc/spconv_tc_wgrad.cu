@@ -1,6 +1,6 @@
 // K4-TC weight gradient of the sparse convolution on tcgen05 tensor cores (sm_100a).
 //
-//   dW[k][ci][co] = sum_o in[nbr[o,k]][ci] * g[o][co]                     Cin, Cout in {32, 64}
+//   dW[k][ci][co] = sum_o in[nbr[o,k]][ci] * g[o][co]                     Cin, Cout in {16, 32, 64}
 //
 // Per kernel offset this is a [Cin x rows] x [rows x Cout] product whose reduction dimension is the
 // row index.  The gathered input rows [row][ci] and the gradient rows [row][co] are exactly the
@@ -62,7 +62,7 @@ struct WgCfg {
     static constexpr int MEMB = 128 / CIN;                          // offsets stacked along M
     static constexpr int MAXG = 512 / COUT > 7 ? 7 : 512 / COUT;    // accumulators per CTA (TMEM columns)
     static constexpr int A_BYTES = WG_STEP * 128 * 4;               // one of {hi, lo}: [64 rows x 128 m]
-    static constexpr int G_BYTES = WG_STEP * COUT * 4;              // one of {hi, lo}: [64 rows x Cout]
+    static constexpr int G_BYTES = WG_STEP * (COUT < 32 ? 32 : COUT) * 4;   // one of {hi, lo}: [64 rows x Cout], 128-B rows
     static constexpr int TOTAL = WG_ASTAGES * 2 * A_BYTES + WG_GSTAGES * 2 * G_BYTES + 256 + 1024;
 };
 
@@ -271,6 +271,12 @@ int launch_wgrad(const float* in, const float* g, const int* nbr, int n_cap, con
 
 using namespace rslo;
 
+extern "C" int rslo_spconv_tc_wgrad_supported(int Cin, int Cout)
+{
+    const bool ci = Cin == 16 || Cin == 32 || Cin == 64, co = Cout == 16 || Cout == 32 || Cout == 64;
+    return ci && co && !(Cin == 16 && Cout == 64) && !(Cin == 64 && Cout == 16);
+}
+
 extern "C" int rslo_spconv_tc_backward_weight(const float* in, const float* grad_out, const int32_t* nbr, int n_out_cap,
                                               const int32_t* n_out_dev, int K, int Cin, int Cout, float* grad_weight,
                                               rslo_stream_t stream)
@@ -278,6 +284,9 @@ extern "C" int rslo_spconv_tc_backward_weight(const float* in, const float* grad
     cudaStream_t st = (cudaStream_t)stream;
     RSLO_CHECK(cudaMemsetAsync(grad_weight, 0, (size_t)K * Cin * Cout * sizeof(float), st));
     if (n_out_cap <= 0) return 0;
+    if (Cin == 16 && Cout == 16) return launch_wgrad<16, 16>(in, grad_out, nbr, n_out_cap, n_out_dev, K, grad_weight, st);
+    if (Cin == 16 && Cout == 32) return launch_wgrad<16, 32>(in, grad_out, nbr, n_out_cap, n_out_dev, K, grad_weight, st);
+    if (Cin == 32 && Cout == 16) return launch_wgrad<32, 16>(in, grad_out, nbr, n_out_cap, n_out_dev, K, grad_weight, st);
     if (Cin == 64 && Cout == 64) return launch_wgrad<64, 64>(in, grad_out, nbr, n_out_cap, n_out_dev, K, grad_weight, st);
     if (Cin == 64 && Cout == 32) return launch_wgrad<64, 32>(in, grad_out, nbr, n_out_cap, n_out_dev, K, grad_weight, st);
     if (Cin == 32 && Cout == 64) return launch_wgrad<32, 64>(in, grad_out, nbr, n_out_cap, n_out_dev, K, grad_weight, st);

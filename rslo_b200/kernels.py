@@ -345,6 +345,10 @@ def spconv_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=T
     return gw, gb
 
 
+def spconv_tc_wgrad_supported(Cin, Cout):
+    return bool(lib.rslo_spconv_tc_wgrad_supported(int(Cin), int(Cout)))
+
+
 @_profiled("spconv_tc_wgrad", _cost_spconv_bwd_weight)
 def spconv_tc_backward_weight(feat, grad_out, nbr, n_out, weight_shape, need_bias=False):
     """dW on the tcgen05 tensor cores (split-TF32); Cin, Cout in {32, 64}."""

@@ -179,7 +179,7 @@ class _SpConvFn(torch.autograd.Function):
             else:
                 gi = K.spconv_backward_data(g, nbr_t, n_in, weight, e.mirror)
         if ctx.needs_input_grad[1]:
-            if ctx.tc:
+            if USE_TC and K.spconv_tc_wgrad_supported(weight.shape[-2], weight.shape[-1]):
                 gw = K.spconv_tc_backward_weight(feat, g, nbr, n_out, weight.shape)
             else:
                 gw, _ = K.spconv_backward_weight(feat, g, nbr, n_out, weight.shape, need_bias=False)

@@ -340,7 +340,8 @@ def test_kth_threshold_matches_torch(K, n):
 
 @pytest.mark.parametrize("cin,cout,K_,n_out", [(64, 64, 27, 2577), (32, 32, 27, 2577), (32, 64, 27, 2577),
                                                (64, 32, 27, 2577), (64, 64, 3, 2577), (64, 64, 27, 39188),
-                                               (64, 64, 27, 50)])
+                                               (64, 64, 27, 50), (16, 16, 27, 80001), (16, 32, 27, 2577),
+                                               (32, 16, 27, 2577)])
 def test_spconv_tensor_core_wgrad(K, cin, cout, K_, n_out):
     """tcgen05 weight-gradient kernel (MN-major operands, offsets stacked along M) vs autograd of the oracle."""
     g = torch.Generator().manual_seed(cin * 7 + cout + K_ + n_out)
