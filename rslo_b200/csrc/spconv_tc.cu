@@ -1,6 +1,6 @@
 // K4-TC: sparse 3-D convolution as an implicit GEMM on the 5th-gen tensor cores (sm_100a, tcgen05).
 //
-//   out[o,:] = act(bias + sum_k in[nbr[o,k],:] @ W[k])        Cin, Cout in {32, 64, 128, 192, 256, 512}
+//   out[o,:] = act(bias + sum_k in[nbr[o,k],:] @ W[k])        Cin, Cout in {16, 32, 64, 128, 192, 256, 512}
 //
 // One CTA owns 128 output rows (one TMEM lane per row) and a 64- (or 32-) wide slice of Cout (blockIdx.z).  For every kernel offset
 // k that at least one of its rows uses, the producer warps gather the 128 neighbour rows (zeros
@@ -43,18 +43,21 @@ __global__ void k_tc_prep(const float* __restrict__ W, int K, int Cin, int Cout,
                           int ntile, float* __restrict__ img)
 {
     const int NDIM = transpose ? Cin : Cout, KDIM = transpose ? Cout : Cin;
-    const int per = NDIM * KDIM;
+    const int KPAD = (KDIM + 31) & ~31;                  // 16-channel inputs are zero-padded to one 32-wide block
+    const int per = NDIM * KPAD;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= K * per) return;
-    const int k = t / per, e = t % per, n = e / KDIM, kk = e % KDIM;
-    float v;
-    if (!transpose) v = W[((size_t)k * Cin + kk) * Cout + n];
-    else v = W[((size_t)(mirror ? K - 1 - k : k) * Cin + n) * Cout + kk];
+    const int k = t / per, e = t % per, n = e / KPAD, kk = e % KPAD;
+    float v = 0.f;
+    if (kk < KDIM) {
+        if (!transpose) v = W[((size_t)k * Cin + kk) * Cout + n];
+        else v = W[((size_t)(mirror ? K - 1 - k : k) * Cin + n) * Cout + kk];
+    }
     const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
     // image: per N tile nt (ntile output channels), per offset k, per 32-wide K block kb:
     //        {B_hi [ntile x 32], B_lo [ntile x 32]}, each SWIZZLE_128B K-major
     const int kb = kk >> 5, nt = n / ntile, nn = n % ntile;
-    char* base = (char*)img + (((size_t)nt * K + k) * (KDIM / 32) + kb) * (size_t)(2 * ntile * 128);
+    char* base = (char*)img + (((size_t)nt * K + k) * (KPAD / 32) + kb) * (size_t)(2 * ntile * 128);
     const uint32_t off = sw128_offset(nn, kk & 31, ntile);
     *(float*)(base + off) = hi;
     *(float*)(base + (size_t)ntile * 128 + off) = lo;
@@ -97,7 +100,8 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     uint32_t* s_mask = s_tmem + 1;
     int* s_last = (int*)(s_tmem + 2);
     int* s_klist = (int*)(s_tmem + 3);        // [27]
-    constexpr int NSUB = KDIM / TC_KS;        // pipeline steps per kernel offset
+    constexpr int KPAD = (KDIM + TC_KS - 1) / TC_KS * TC_KS;   // 16 real channels occupy one zero-padded 32-wide step
+    constexpr int NSUB = KPAD / TC_KS;        // pipeline steps per kernel offset
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = dev_count(n_dev, n_cap);
@@ -105,9 +109,9 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     const int split = gridDim.y, sidx = blockIdx.y;
     const int ntile = blockIdx.z;             // this CTA's slice of NDIM output channels (n_total = gridDim.z * NDIM)
     const int wtile = blockIdx.x * gridDim.z + ntile;          // work tile id (rows x channel slice)
-    bimg += (size_t)ntile * K * (KDIM / TC_KS) * (2 * S::B_BYTES / 4);
+    bimg += (size_t)ntile * K * NSUB * (2 * S::B_BYTES / 4);
     if (row0 >= n) return;                    // uniform per CTA (all splits of the tile agree)
-    constexpr int TCOLS = 2 * NDIM;           // two accumulator buffers (64 or 128 columns: powers of two)
+    constexpr int TCOLS = 2 * NDIM;           // two accumulator buffers (32, 64 or 128 columns: powers of two)
 
     if (tid == 0) {
         for (int i = 0; i < TC_STAGES; ++i) {
@@ -183,7 +187,8 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 const int src = s_nbr[r * K + k];
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #if TC_DIAG != 3
-                if (src >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM + h * TC_KS) + c);
+                if (src >= 0 && h * TC_KS + c * 4 < KDIM)
+                    v[j] = __ldg(reinterpret_cast<const float4*>(in + (size_t)src * KDIM + h * TC_KS) + c);
 #endif
             }
         };
@@ -387,10 +392,10 @@ int launch_tc(const float* in, const int* nbr, int n_cap, const int* n_dev, int 
 }
 
 // output-channel tile of a layer: 64 where it divides, else 32
-static inline int tc_ntile(int ndim) { return ndim % 64 == 0 ? 64 : 32; }
+static inline int tc_ntile(int ndim) { return ndim % 64 == 0 ? 64 : (ndim % 32 == 0 ? 32 : 16); }
 static inline bool tc_kdim_ok(int kdim)
 {
-    return kdim == 32 || kdim == 64 || kdim == 128 || kdim == 192 || kdim == 256 || kdim == 512;
+    return kdim == 16 || kdim == 32 || kdim == 64 || kdim == 128 || kdim == 192 || kdim == 256 || kdim == 512;
 }
 
 }  // namespace
@@ -404,7 +409,11 @@ extern "C" int rslo_spconv_tc_supported(int Cin, int Cout, int K)
     return tc_kdim_ok(Cin) && tc_kdim_ok(Cout) && K >= 1 && K <= 27;
 }
 
-extern "C" size_t rslo_spconv_tc_image_bytes(int K, int Cin, int Cout) { return (size_t)K * Cin * Cout * 8; }
+extern "C" size_t rslo_spconv_tc_image_bytes(int K, int Cin, int Cout)
+{
+    const int a = (Cin + 31) & ~31, b = (Cout + 31) & ~31;       // either dimension may be the (padded) K side
+    return (size_t)K * a * b * 8;
+}
 
 extern "C" int rslo_spconv_tc_prepare(const float* weight, int K, int Cin, int Cout, int transpose, int mirror,
                                       float* image, rslo_stream_t stream)
@@ -413,8 +422,8 @@ extern "C" int rslo_spconv_tc_prepare(const float* weight, int K, int Cin, int C
         set_last_error("rslo_spconv_tc_prepare: unsupported shape", cudaErrorInvalidValue);
         return (int)cudaErrorInvalidValue;
     }
-    const int tot = K * Cin * Cout;
-    const int ndim = transpose ? Cin : Cout;
+    const int ndim = transpose ? Cin : Cout, kdim = transpose ? Cout : Cin;
+    const int tot = K * ndim * ((kdim + 31) & ~31);
     RSLO_COUNT();
     k_tc_prep<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, Cin, Cout, transpose, mirror, tc_ntile(ndim),
                                                                image);
@@ -449,9 +458,13 @@ extern "C" int rslo_spconv_tc_forward(const float* in, const int32_t* nbr, int n
         if (nt == 64)                                                                                             \
             return launch_tc<KD, 64>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, ndim,       \
                                      workspace, workspace_bytes, st);                                             \
-        return launch_tc<KD, 32>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, ndim, workspace, \
+        if (nt == 32)                                                                                             \
+            return launch_tc<KD, 32>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, ndim,       \
+                                     workspace, workspace_bytes, st);                                             \
+        return launch_tc<KD, 16>(in, nbr, n_out_cap, n_out_dev, K, image, bias, act, slope, out, ndim, workspace, \
                                  workspace_bytes, st);                                                            \
     }
+    RSLO_TC_CASE(16)
     RSLO_TC_CASE(32)
     RSLO_TC_CASE(64)
     RSLO_TC_CASE(128)

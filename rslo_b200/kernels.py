@@ -282,7 +282,7 @@ def spconv_tc_prepare(weight, transpose=False, mirror=False):
     """W [K,Cin,Cout] -> pre-swizzled 3xTF32 {hi, lo} image for csrc/spconv_tc.cu."""
     w = _f32(weight.contiguous())
     Kk, Cin, Cout = w.shape[-3] if w.dim() == 3 else w.numel() // (w.shape[-2] * w.shape[-1]), w.shape[-2], w.shape[-1]
-    img = torch.empty(Kk * Cin * Cout * 2, dtype=torch.float32, device=w.device)
+    img = torch.empty(lib.rslo_spconv_tc_image_bytes(Kk, Cin, Cout) // 4, dtype=torch.float32, device=w.device)
     check(lib.rslo_spconv_tc_prepare(ptr(w), Kk, Cin, Cout, 1 if transpose else 0, 1 if mirror else 0, ptr(img),
                                      stream()), "rslo_spconv_tc_prepare")
     _count()

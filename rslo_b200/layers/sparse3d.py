@@ -147,7 +147,9 @@ class _SpConvFn(torch.autograd.Function):
         n_out = entry.n_in if inverse else entry.n_out
         feat = feat.contiguous()
         Kk, Cin, Cout = weight.shape
-        ctx.tc = USE_TC and K.spconv_tc_supported(Cin, Cout, Kk)
+        # 16-channel layers: the tensor-core forward works (tested) but is slower than the FFMA kernel there
+        # (half of each 32-wide K step is padding; measured 34.8 vs 32.2 ms/step), so only >= 32 channels use it
+        ctx.tc = USE_TC and min(Cin, Cout) >= 32 and K.spconv_tc_supported(Cin, Cout, Kk)
         if ctx.tc:
             ctx.images = images if images is not None else _ImageCache()
             img = ctx.images.get(weight, False, False)

@@ -227,7 +227,8 @@ def test_nn_bit_exact(K, scan_pair, n, m, kind):
 
 @pytest.mark.parametrize("cin,cout,K_,n_out", [(64, 64, 27, 2577), (32, 32, 27, 2577), (32, 64, 27, 2577),
                                                (64, 32, 27, 2577), (64, 64, 3, 2577), (64, 64, 27, 19594),
-                                               (32, 32, 27, 40001)])
+                                               (32, 32, 27, 40001), (16, 16, 27, 2577), (16, 32, 27, 2577),
+                                               (32, 16, 27, 2577), (16, 16, 27, 80001)])
 def test_spconv_tensor_core_forward(K, cin, cout, K_, n_out):
     """tcgen05 split-TF32 implicit-GEMM kernel vs the oracle's gather-conv: FP32-level agreement.
     Row counts cover the offset-split paths (4-way, 2-way) and the unsplit one."""
