@@ -156,6 +156,36 @@ int rslo_spconv_tc_backward_weight(const float* in, const float* grad_out, const
                                    const int32_t* n_out_dev, int K, int Cin, int Cout, float* grad_weight,
                                    rslo_stream_t stream);
 
+/* ---- a8: dense 2-D convolutions of the odometry head (csrc/conv2d_tc.cu) ---------------------------
+ * Replaces cuDNN under rslo/models/odom_pred_base.py:155-276, rslo/layers/MaskConv.py:53-63,
+ * rslo/models/custom_resnet_spc.py:224-298: 3x3 (pad 1) and 1x1 (pad 0), stride 1 or 2, groups 1,
+ * Cin and Cout multiples of 32.  tcgen05.mma kind::tf32 with the 3xTF32 operand split (FP32-level
+ * accuracy), operands staged by TMA tensor tiles (image border = TMA zero fill).
+ * Activations are NHWC "split pairs" [2][B][H][W][C]: plane 0 = hi = RN_tf32(x), plane 1 = x - hi
+ * (rslo_conv2d_split makes one from a plain NHWC tensor).  Weights are OIHW as in the reference's
+ * state_dict; rslo_conv2d_tc_prepare makes the split image [2][k*k][N][Kd] once per weight update
+ * (mode 0: forward, N = Cout, Kd = Cin; mode 1: data gradient, N = Cin, Kd = Cout), 8*k*k*Cin*Cout bytes.
+ * workspace: rslo_conv2d_tc_workspace_bytes bytes, ZEROED once by the caller before first use and then
+ * reused on one stream (split-K tile counters; the kernels leave them zeroed). */
+int rslo_conv2d_tc_supported(int Cin, int Cout, int ksize, int stride);
+int rslo_conv2d_split(const float* x, size_t n, float* split_pair, rslo_stream_t stream);
+int rslo_conv2d_tc_prepare(const float* weight_oihw, int Cout, int Cin, int ksize, int mode, float* image,
+                           rslo_stream_t stream);
+size_t rslo_conv2d_tc_workspace_bytes(int B, int H, int W, int Cmax);
+/* y [B][Ho][Wo][Cout] = conv(x) (+ bias, may be NULL) (ReLU when relu != 0) */
+int rslo_conv2d_tc_forward(const float* x_split, int B, int H, int W, int Cin, const float* image, int Cout,
+                           int ksize, int stride, const float* bias, int relu, float* y, void* workspace,
+                           size_t workspace_bytes, rslo_stream_t stream);
+/* dx [B][H][W][Cin] from g_split [2][B][Ho][Wo][Cout] and the mode-1 image */
+int rslo_conv2d_tc_backward_data(const float* g_split, int B, int H, int W, int Cin, const float* image_t, int Cout,
+                                 int ksize, int stride, float* dx, void* workspace, size_t workspace_bytes,
+                                 rslo_stream_t stream);
+/* grad_weight_oihw [Cout][Cin][k][k] (= , or += when accumulate) ; scratch: rslo_conv2d_tc_wgrad_scratch_bytes */
+size_t rslo_conv2d_tc_wgrad_scratch_bytes(int Cin, int Cout, int ksize);
+int rslo_conv2d_tc_backward_weight(const float* x_split, const float* g_split, int B, int H, int W, int Cin, int Cout,
+                                   int ksize, int stride, float* scratch, int accumulate, float* grad_weight_oihw,
+                                   rslo_stream_t stream);
+
 /* ---- a7: SparseConvTensor.dense() + view (middle.py:240-243) ------------------------------------
  * feat [n,C] at sites of a (D,H,W) level -> dense [C*D, H, W] f32 (zero where no site). */
 int rslo_dense_from_sites(const float* feat, int C, const uint32_t* cells, const int32_t* perm,

@@ -472,3 +472,112 @@ def cov_residual(pred, target, cov_pred, cov_target, R, idx, dist, thr, reg_weig
     cov_pred, cov_target (rslo/core/losses.py:348-363, 401-435)."""
     return _CovResidualFn.apply(pred, target, cov_pred, cov_target, R, _i32(idx), _f32(dist), _f32(thr.reshape(1)),
                                 reg_weight)
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: dense 2-D convolutions of the head (csrc/conv2d_tc.cu): TMA-staged split-TF32 tcgen05 implicit GEMM
+# ------------------------------------------------------------------------------------------------
+def conv2d_tc_supported(cin, cout, ksize, stride):
+    return bool(lib.rslo_conv2d_tc_supported(cin, cout, ksize, stride))
+
+
+_CONV_WS = {}
+
+
+def _conv_ws():
+    """Per-(device, stream) split-K workspace of the dense convolutions; zeroed once (the kernels keep the
+    tile counters zeroed between launches)."""
+    dev = torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    ws = _CONV_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(lib.rslo_conv2d_tc_workspace_bytes(0, 0, 0, 0), dtype=torch.uint8, device=f"cuda:{dev}")
+        _CONV_WS[key] = ws
+    return ws
+
+
+def conv2d_split(x_nhwc, out=None):
+    """x [B,H,W,C] f32 contiguous -> split pair [2,B,H,W,C] (hi = RN_tf32(x), lo = x - hi)."""
+    x = _f32(x_nhwc)
+    if out is None:
+        out = torch.empty((2,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+    check(lib.rslo_conv2d_split(ptr(x), x.numel(), ptr(out), stream()), "rslo_conv2d_split")
+    _count()
+    return out
+
+
+def conv2d_tc_prepare(weight_oihw, mode, out=None):
+    """OIHW weight -> split image [2, k*k, N, Kd] (mode 0 forward: N=Cout, Kd=Cin; mode 1 data gradient)."""
+    w = _f32(weight_oihw.detach().contiguous())
+    cout, cin, ks, _ = w.shape
+    if out is None:
+        out = torch.empty(2 * ks * ks * cin * cout, dtype=torch.float32, device=w.device)
+    check(lib.rslo_conv2d_tc_prepare(ptr(w), cout, cin, ks, mode, ptr(out), stream()), "rslo_conv2d_tc_prepare")
+    _count()
+    return out
+
+
+def _cost_conv2d(out, x_split, image, cout, ksize, stride, *a, **k):
+    _, B, H, W, cin = x_split.shape
+    npx = out.shape[0] * out.shape[1] * out.shape[2]
+    return 4 * (B * H * W * cin + npx * cout + ksize * ksize * cin * cout), 2 * npx * ksize * ksize * cin * cout
+
+
+@_profiled("conv2d_tc", _cost_conv2d)
+def conv2d_tc_forward(x_split, image, cout, ksize, stride, bias=None, relu=False, out=None):
+    """y [B,Ho,Wo,Cout] = conv(x) (+bias)(ReLU); x_split [2,B,H,W,Cin]."""
+    x = _f32(x_split)
+    _, B, H, W, cin = x.shape
+    pad = ksize // 2
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x.device)
+    ws = _conv_ws()
+    check(lib.rslo_conv2d_tc_forward(ptr(x), B, H, W, cin, ptr(image), cout, ksize, stride, ptr(bias), 1 if relu else 0,
+                                     ptr(out), ptr(ws), ws.numel(), stream()), "rslo_conv2d_tc_forward")
+    _count()
+    return out
+
+
+def _cost_conv2d_bwd(out, g_split, image_t, in_shape, ksize, stride, *a, **k):
+    _, B, Ho, Wo, cout = g_split.shape
+    _, H, W, cin = in_shape
+    return 4 * (B * H * W * cin + B * Ho * Wo * cout + ksize * ksize * cin * cout), 2 * B * Ho * Wo * ksize * ksize * cin * cout
+
+
+@_profiled("conv2d_tc_dgrad", _cost_conv2d_bwd)
+def conv2d_tc_backward_data(g_split, image_t, in_shape, ksize, stride, out=None):
+    """dx [B,H,W,Cin] from g_split [2,B,Ho,Wo,Cout] and the mode-1 weight image."""
+    g = _f32(g_split)
+    B, H, W, cin = in_shape
+    cout = g.shape[-1]
+    if out is None:
+        out = torch.empty((B, H, W, cin), dtype=torch.float32, device=g.device)
+    ws = _conv_ws()
+    check(lib.rslo_conv2d_tc_backward_data(ptr(g), B, H, W, cin, ptr(image_t), cout, ksize, stride, ptr(out), ptr(ws),
+                                           ws.numel(), stream()), "rslo_conv2d_tc_backward_data")
+    _count()
+    return out
+
+
+def _cost_conv2d_wgrad(out, x_split, g_split, ksize, stride, *a, **k):
+    _, B, H, W, cin = x_split.shape
+    _, _, Ho, Wo, cout = g_split.shape
+    return 4 * (B * H * W * cin + B * Ho * Wo * cout + ksize * ksize * cin * cout), 2 * B * Ho * Wo * ksize * ksize * cin * cout
+
+
+@_profiled("conv2d_tc_wgrad", _cost_conv2d_wgrad)
+def conv2d_tc_backward_weight(x_split, g_split, ksize, stride, out=None, accumulate=False):
+    """grad_weight OIHW [Cout,Cin,k,k] from x_split [2,B,H,W,Cin] and g_split [2,B,Ho,Wo,Cout]."""
+    x, g = _f32(x_split), _f32(g_split)
+    _, B, H, W, cin = x.shape
+    cout = g.shape[-1]
+    if out is None:
+        assert not accumulate
+        out = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    scratch = workspace(lib.rslo_conv2d_tc_wgrad_scratch_bytes(cin, cout, ksize), "conv2d_wgrad")
+    check(lib.rslo_conv2d_tc_backward_weight(ptr(x), ptr(g), B, H, W, cin, cout, ksize, stride, ptr(scratch),
+                                             1 if accumulate else 0, ptr(out), stream()),
+          "rslo_conv2d_tc_backward_weight")
+    _count()
+    return out
