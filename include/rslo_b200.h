@@ -169,22 +169,82 @@ int rslo_spconv_tc_backward_weight(const float* in, const float* grad_out, const
  * reused on one stream (split-K tile counters; the kernels leave them zeroed). */
 int rslo_conv2d_tc_supported(int Cin, int Cout, int ksize, int stride);
 int rslo_conv2d_split(const float* x, size_t n, float* split_pair, rslo_stream_t stream);
-int rslo_conv2d_tc_prepare(const float* weight_oihw, int Cout, int Cin, int ksize, int mode, float* image,
-                           rslo_stream_t stream);
+int rslo_conv2d_tc_prepare(const float* weight_oihw, int Cout, int Cout_padded, int Cin, int ksize, int mode,
+                           float* image, rslo_stream_t stream);
 size_t rslo_conv2d_tc_workspace_bytes(int B, int H, int W, int Cmax);
-/* y [B][Ho][Wo][Cout] = conv(x) (+ bias, may be NULL) (ReLU when relu != 0) */
+/* y [B][Ho][Wo][Cout] = conv(x) (+ bias, may be NULL) (ReLU when relu != 0).  stats (may be NULL):
+ * double [B / imgs_per_group][Cout][2], pre-zeroed; the epilogue adds the per-channel sum and sum of squares of
+ * y over each statistics group of images (the BatchNorm batch statistics of the layer that follows).
+ * Narrow heads (7 / 1 output channels): prepare with Cout_padded = 32 and pass Cout = 32 here. */
 int rslo_conv2d_tc_forward(const float* x_split, int B, int H, int W, int Cin, const float* image, int Cout,
-                           int ksize, int stride, const float* bias, int relu, float* y, void* workspace,
-                           size_t workspace_bytes, rslo_stream_t stream);
-/* dx [B][H][W][Cin] from g_split [2][B][Ho][Wo][Cout] and the mode-1 image */
+                           int ksize, int stride, const float* bias, int relu, float* y, double* stats,
+                           int imgs_per_group, void* workspace, size_t workspace_bytes, rslo_stream_t stream);
+/* dx [B][H][W][Cin] (= , or += when accumulate) from g_split [2][B][Ho][Wo][Cout] and the mode-1 image */
 int rslo_conv2d_tc_backward_data(const float* g_split, int B, int H, int W, int Cin, const float* image_t, int Cout,
-                                 int ksize, int stride, float* dx, void* workspace, size_t workspace_bytes,
-                                 rslo_stream_t stream);
-/* grad_weight_oihw [Cout][Cin][k][k] (= , or += when accumulate) ; scratch: rslo_conv2d_tc_wgrad_scratch_bytes */
+                                 int ksize, int stride, float* dx, int accumulate, void* workspace,
+                                 size_t workspace_bytes, rslo_stream_t stream);
+/* grad_weight_oihw [Cout_real][Cin][k][k] (= , or += when accumulate); g_split has Cout (padded) channels;
+ * scratch: rslo_conv2d_tc_wgrad_scratch_bytes(Cin, Cout, ksize) floats laid out [k*k][Cin][Cout].
+ * grad_weight_oihw == NULL: the products are ADDED into scratch (which the caller zeroed) and left there for
+ * rslo_conv2d_multi_wgrad_finish — one memset and one finish launch for all convolutions of a backward pass. */
 size_t rslo_conv2d_tc_wgrad_scratch_bytes(int Cin, int Cout, int ksize);
 int rslo_conv2d_tc_backward_weight(const float* x_split, const float* g_split, int B, int H, int W, int Cin, int Cout,
-                                   int ksize, int stride, float* scratch, int accumulate, float* grad_weight_oihw,
-                                   rslo_stream_t stream);
+                                   int ksize, int stride, int Cout_real, float* scratch, int accumulate,
+                                   float* grad_weight_oihw, rslo_stream_t stream);
+
+/* Table-driven variants (device arrays of these structs): weight images (+ zero-padded bias) of n convolutions in
+ * one launch; [k*k][Cin][CoutP] weight-gradient scratch -> OIHW gradients of n convolutions in one launch. */
+typedef struct {
+    const float* w;        /* OIHW [Cout][Cin][k][k] */
+    float* img_fwd;        /* mode-0 image [2][taps][CoutP][Cin] or NULL */
+    float* img_bwd;        /* mode-1 image [2][taps][Cin][CoutP] or NULL */
+    const float* bias;     /* [Cout] or NULL */
+    float* bias_pad;       /* [CoutP] or NULL */
+    int Cout, CoutP, Cin, taps;
+} rslo_conv_prep_t;
+typedef struct {
+    const float* dW;       /* [taps][Cin][CoutP] */
+    float* gw;             /* OIHW [Cout][Cin][taps] */
+    int Cout, CoutP, Cin, taps;
+} rslo_wgrad_finish_t;
+int rslo_conv2d_multi_prepare(const rslo_conv_prep_t* table_dev, int n, rslo_stream_t stream);
+int rslo_conv2d_multi_wgrad_finish(const rslo_wgrad_finish_t* table_dev, int n, rslo_stream_t stream);
+
+/* ---- a8: what the head does between its convolutions (csrc/head_ops.cu), NHWC -------------------------------
+ * Frame-pair input (rslo/models/odom_pred.py:165-170): x1, x2 [B][C][HW] (NCHW BEV maps of the two frames) ->
+ * split pair [2][B][HW][2C] of cat(x1, x2) and mask [B][HW] = (sum_c x1 != 0); and the gradient's way back. */
+int rslo_head_pack_input(const float* x1, const float* x2, int B, int C, int HW, float* split_pair, float* mask,
+                         rslo_stream_t stream);
+int rslo_head_unpack_grad(const float* dx, int B, int C, int HW, float* g1, float* g2, rslo_stream_t stream);
+/* BatchNorm2d (+ residual) (+ ReLU) over y [B][HW][C] (SPC_SyncBN2d / SPC_ReLU / BasicBlock,
+ * rslo/layers/SparseConv.py:96-132, rslo/models/custom_resnet_spc.py:224-298).
+ * stats != NULL: batch statistics, double [G][C][2] = {sum, sum of squares} per statistics group of
+ * imgs_per_group images (G = B / imgs_per_group) as accumulated by rslo_conv2d_tc_forward; running_mean/var
+ * (may be NULL) are updated group after group, update_repeat times each (momentum, unbiased variance), and
+ * num_batches_tracked += G * update_repeat.  stats == NULL: running statistics (eval / frozen BN).
+ * Outputs (each may be NULL): z [B][HW][C]; z_split [2][B][HW][C]; mean_rstd float [G][C][2] for the backward. */
+int rslo_bn_act_forward(const float* y, int B, int HW, int C, int imgs_per_group, const double* stats,
+                        const float* gamma, const float* beta, float* running_mean, float* running_var,
+                        long long* num_batches_tracked, float eps, float momentum, int update_repeat,
+                        const float* residual, int relu, float* z, float* z_split, float* mean_rstd,
+                        rslo_stream_t stream);
+/* Backward of the above: dz (gradient w.r.t. z), z (only read when relu), y, mean_rstd, gamma ->
+ * g_split [2][B][HW][C] (gradient w.r.t. y as a split pair, the operand of the convolution backward kernels),
+ * dres (may be NULL; = or += the gradient w.r.t. the residual), dgamma / dbeta [C], dbias [C] (may be NULL: gradient
+ * of a bias added before the normalisation).  sums: double [G][C][2] scratch, ZEROED by the caller. */
+int rslo_bn_act_backward(const float* dz, const float* z, const float* y, int B, int HW, int C, int imgs_per_group,
+                         const float* mean_rstd, const float* gamma, int relu, int batch_stats, double* sums,
+                         float* g_split, float* dres, int dres_accumulate, float* dgamma, float* dbeta, float* dbias,
+                         rslo_stream_t stream);
+/* nn.Upsample(scale_factor=up, nearest) of z [B][H][W][C] written as channels [choff, choff+C) of the split pair
+ * [2][B][up*H][up*W][ld] (torch.cat + Upsample of the decoder, rslo/models/odom_pred_base.py:196-207), and back:
+ * dz [B][H][W][C] (= or +=) sum over each up x up block of dcat [B][up*H][up*W][ld] channels [choff, choff+C). */
+int rslo_upcat_split(const float* z, int B, int H, int W, int C, int up, int ld, int choff, float* dst_split,
+                     rslo_stream_t stream);
+int rslo_upcat_backward(const float* dcat, int B, int H, int W, int C, int up, int ld, int choff, float* dz,
+                        int accumulate, rslo_stream_t stream);
+/* out[c] += sum_rows g[row][c] for c < C <= 32, g [N][ld] (bias gradient of the 7- / 1-channel output convs) */
+int rslo_bias_grad(const float* g, int N, int ld, int C, float* out, rslo_stream_t stream);
 
 /* ---- a7: SparseConvTensor.dense() + view (middle.py:240-243) ------------------------------------
  * feat [n,C] at sites of a (D,H,W) level -> dense [C*D, H, W] f32 (zero where no site). */

@@ -50,12 +50,21 @@ SIGNATURES = {
     "rslo_spconv_tc_backward_weight": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rslo_conv2d_tc_supported": (_i, [_i, _i, _i, _i]),
     "rslo_conv2d_split": (_i, [_vp, _sz, _vp, _vp]),
-    "rslo_conv2d_tc_prepare": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "rslo_conv2d_tc_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rslo_conv2d_tc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "rslo_conv2d_tc_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
-    "rslo_conv2d_tc_backward_data": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "rslo_conv2d_tc_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _sz, _vp]),
+    "rslo_conv2d_tc_backward_data": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "rslo_conv2d_tc_wgrad_scratch_bytes": (_sz, [_i, _i, _i]),
-    "rslo_conv2d_tc_backward_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "rslo_conv2d_tc_backward_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "rslo_conv2d_multi_prepare": (_i, [_vp, _i, _vp]),
+    "rslo_conv2d_multi_wgrad_finish": (_i, [_vp, _i, _vp]),
+    "rslo_head_pack_input": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rslo_head_unpack_grad": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rslo_bn_act_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rslo_bn_act_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rslo_upcat_split": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rslo_upcat_backward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "rslo_bias_grad": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "rslo_dense_from_sites": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rslo_kabsch_workspace_bytes": (_sz, []),
     "rslo_kabsch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

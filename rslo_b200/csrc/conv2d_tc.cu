@@ -50,6 +50,8 @@ struct ConvParams {
     int OH, OW, osh, ooh, osw, oow, ldo;
     int group;
     int relu;
+    int accumulate;                 // epilogue adds to the destination instead of overwriting it
+    int stats_c, imgs_per_group;    // BN-statistics epilogue: channels of the stats table, images per statistics group
 };
 
 template <int NT>
@@ -67,7 +69,7 @@ template <int NT>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ ConvParams P, const float* __restrict__ bias, float* __restrict__ out,
-            float* __restrict__ scratch, int* __restrict__ tile_counter)
+            float* __restrict__ scratch, int* __restrict__ tile_counter, double* __restrict__ stats)
 {
     using S = CvCfg<NT>;
     constexpr int STAGES = S::STAGES;
@@ -224,20 +226,51 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         const int wl = r & (P.Wt - 1), hl = r >> P.wt_log2;
         const int h = h0 + hl, w = w0 + wl;
-        if (finish && h < P.gridH && w < P.gridW) {
-            float4* dst = reinterpret_cast<float4*>(
-                out + (((size_t)b * P.OH + (size_t)(h * P.osh + P.ooh)) * P.OW + (size_t)(w * P.osw + P.oow)) * P.ldo + n0);
+        const bool valid = h < P.gridH && w < P.gridW;
+        if (finish) {
+            if (bias) {
 #pragma unroll
-            for (int i = 0; i < NT; i += 4) {
-                float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-                if (bias) {
+                for (int i = 0; i < NT; i += 4) {
                     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + i));
-                    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    acc[i] += bv.x; acc[i + 1] += bv.y; acc[i + 2] += bv.z; acc[i + 3] += bv.w;
                 }
-                if (P.relu) {
-                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(
+                    out + (((size_t)b * P.OH + (size_t)(h * P.osh + P.ooh)) * P.OW + (size_t)(w * P.osw + P.oow)) * P.ldo + n0);
+#pragma unroll
+                for (int i = 0; i < NT; i += 4) {
+                    float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                    if (P.relu) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                    if (P.accumulate) {
+                        const float4 o = dst[i / 4];
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                    dst[i / 4] = v;
                 }
-                dst[i / 4] = v;
+            }
+            if (stats != nullptr) {
+                // per-channel sum / sum of squares of this tile's valid pixels (BatchNorm batch statistics of the
+                // statistics group the image belongs to): transpose through the now idle pipeline stages
+                float* tile = reinterpret_cast<float*>(smem);
+                constexpr int LD = NT + 1;
+#pragma unroll
+                for (int i = 0; i < NT; ++i) tile[r * LD + i] = valid ? acc[i] : 0.f;
+                drain_sync();
+                double* dst = stats + ((size_t)(b / P.imgs_per_group) * P.stats_c + n0) * 2;
+                for (int c = r; c < NT; c += CV_ROWS) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                    for (int row = 0; row < CV_ROWS; ++row) {
+                        const float v = tile[row * LD + c];
+                        s1 += v;
+                        s2 = fmaf(v, v, s2);
+                    }
+                    atomicAdd(dst + 2 * c, (double)s1);
+                    atomicAdd(dst + 2 * c + 1, (double)s2);
+                }
             }
         }
     }
@@ -285,7 +318,7 @@ static int encode_act(CUtensorMap* tm, const float* base, int B, int H, int W, i
 
 template <int NT>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvParams& P, int tiles, int split, int ntiles,
-                       const float* bias, float* out, float* scratch, int* counter, cudaStream_t st)
+                       const float* bias, float* out, float* scratch, int* counter, double* stats, cudaStream_t st)
 {
     using S = CvCfg<NT>;
     static bool configured = false;
@@ -294,7 +327,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const Con
         configured = true;
     }
     RSLO_COUNT();
-    k_conv2d_tc<NT><<<dim3(tiles, split, ntiles), CV_THREADS, S::TOTAL, st>>>(tmA, tmW, P, bias, out, scratch, counter);
+    k_conv2d_tc<NT><<<dim3(tiles, split, ntiles), CV_THREADS, S::TOTAL, st>>>(tmA, tmW, P, bias, out, scratch, counter, stats);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc");
     return 0;
 }
@@ -321,7 +354,8 @@ constexpr int CV_MAX_COUNTERS = 4096;
 // taps in tile coordinates, output address mapping (OH, OW, osh, ooh, osw, oow, ldo).
 static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, const float* wimg, int nslices, int N,
                     int gridH, int gridW, const ConvTap* taps, int ntaps, float* out, int OH, int OW, int osh, int ooh,
-                    int osw, int oow, int ldo, const float* bias, int relu, void* ws, size_t ws_bytes, cudaStream_t st)
+                    int osw, int oow, int ldo, const float* bias, int relu, void* ws, size_t ws_bytes, cudaStream_t st,
+                    double* stats = nullptr, int imgs_per_group = 1, int accumulate = 0)
 {
     if (C % 32 != 0 || ntaps < 1 || ntaps > CV_MAX_TAPS || (H % Pf) || (W % Pf)) {
         set_last_error("rslo_conv2d_tc: unsupported shape", cudaErrorInvalidValue);
@@ -351,6 +385,9 @@ static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, co
     P.OH = OH; P.OW = OW; P.osh = osh; P.ooh = ooh; P.osw = osw; P.oow = oow; P.ldo = ldo;
     P.group = P.kchunks > 8 ? 8 : P.kchunks;
     P.relu = relu;
+    P.accumulate = accumulate;
+    P.stats_c = N;
+    P.imgs_per_group = imgs_per_group > 0 ? imgs_per_group : 1;
 
     float* scratch = nullptr;
     int* counter = nullptr;
@@ -372,9 +409,9 @@ static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, co
         rc = tma::encode_f32(&tmW, wimg, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    if (NT == 128) return launch_conv<128>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, st);
-    if (NT == 64) return launch_conv<64>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, st);
-    return launch_conv<32>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, st);
+    if (NT == 128) return launch_conv<128>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+    if (NT == 64) return launch_conv<64>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+    return launch_conv<32>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
 }
 
 // forward taps of a ks x ks / stride s / pad (ks/2) convolution read through the parity view (Pf = s)
@@ -412,15 +449,17 @@ __global__ void k_split_planes(const float4* __restrict__ x, size_t n4, float4* 
 
 // OIHW weight -> split image [2][taps][N][Kd]:  mode 0 (forward): N = Cout, Kd = Cin, img[t][co][ci];
 // mode 1 (data gradient): N = Cin, Kd = Cout, img[t][ci][co]
-__global__ void k_conv2d_wprep(const float* __restrict__ w, int Cout, int Cin, int taps, int mode, float* __restrict__ img)
+// (output channels zero-padded to CoutP, a multiple of 32, for the narrow 7- / 1-channel heads)
+__global__ void k_conv2d_wprep(const float* __restrict__ w, int Cout, int CoutP, int Cin, int taps, int mode,
+                               float* __restrict__ img)
 {
-    const int total = taps * Cout * Cin;
+    const int total = taps * CoutP * Cin;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int N = mode ? Cin : Cout, Kd = mode ? Cout : Cin;
+    const int N = mode ? Cin : CoutP, Kd = mode ? CoutP : Cin;
     const int kk = i % Kd, n = (i / Kd) % N, t = i / (Kd * N);
     const int co = mode ? kk : n, ci = mode ? n : kk;
-    const float v = __ldg(w + ((size_t)co * Cin + ci) * taps + t);
+    const float v = co < Cout ? __ldg(w + ((size_t)co * Cin + ci) * taps + t) : 0.f;
     const float h = tf32_rn(v);
     img[i] = h;
     img[(size_t)total + i] = v - h;
@@ -647,13 +686,14 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, const Wg
 }
 
 // dW [taps][Cin][Cout] -> OIHW gradient (+= when accumulate)
-__global__ void k_wgrad_finish(const float* __restrict__ dW, int Cout, int Cin, int taps, int accumulate, float* __restrict__ gw)
+__global__ void k_wgrad_finish(const float* __restrict__ dW, int Cout, int CoutP, int Cin, int taps, int accumulate,
+                               float* __restrict__ gw)
 {
     const int total = taps * Cout * Cin;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;         // OIHW index
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;         // OIHW index (real output channels only)
     if (i >= total) return;
     const int t = i % taps, ci = (i / taps) % Cin, co = i / (taps * Cin);
-    const float v = __ldg(dW + ((size_t)t * Cin + ci) * Cout + co);
+    const float v = __ldg(dW + ((size_t)t * Cin + ci) * CoutP + co);
     gw[i] = accumulate ? gw[i] + v : v;
 }
 
@@ -683,12 +723,14 @@ extern "C" int rslo_conv2d_split(const float* x, size_t n, float* split_pair, rs
     return 0;
 }
 
-extern "C" int rslo_conv2d_tc_prepare(const float* weight_oihw, int Cout, int Cin, int ksize, int mode, float* image,
-                                      rslo_stream_t stream)
+extern "C" int rslo_conv2d_tc_prepare(const float* weight_oihw, int Cout, int Cout_padded, int Cin, int ksize, int mode,
+                                      float* image, rslo_stream_t stream)
 {
-    const int total = ksize * ksize * Cout * Cin;
+    if (Cout_padded < Cout) Cout_padded = Cout;
+    const int total = ksize * ksize * Cout_padded * Cin;
     RSLO_COUNT();
-    k_conv2d_wprep<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(weight_oihw, Cout, Cin, ksize * ksize, mode, image);
+    k_conv2d_wprep<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(weight_oihw, Cout, Cout_padded, Cin, ksize * ksize,
+                                                                      mode, image);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc_prepare");
     return 0;
 }
@@ -701,8 +743,8 @@ extern "C" size_t rslo_conv2d_tc_workspace_bytes(int B, int H, int W, int Cmax)
 }
 
 extern "C" int rslo_conv2d_tc_forward(const float* x_split, int B, int H, int W, int Cin, const float* image, int Cout,
-                                      int ksize, int stride, const float* bias, int relu, float* y, void* workspace,
-                                      size_t workspace_bytes, rslo_stream_t stream)
+                                      int ksize, int stride, const float* bias, int relu, float* y, double* stats,
+                                      int imgs_per_group, void* workspace, size_t workspace_bytes, rslo_stream_t stream)
 {
     if (!rslo_conv2d_tc_supported(Cin, Cout, ksize, stride)) {
         set_last_error("rslo_conv2d_tc_forward: unsupported shape", cudaErrorInvalidValue);
@@ -713,13 +755,13 @@ extern "C" int rslo_conv2d_tc_forward(const float* x_split, int B, int H, int W,
     ConvTap taps[CV_MAX_TAPS];
     const int nt = forward_taps(ksize, stride, Cin, taps);
     return run_conv(x_split, B, H, W, Cin, stride, image, ksize * ksize, Cout, Ho, Wo, taps, nt, y, Ho, Wo, 1, 0, 1, 0, Cout,
-                    bias, relu, workspace, workspace_bytes, (cudaStream_t)stream);
+                    bias, relu, workspace, workspace_bytes, (cudaStream_t)stream, stats, imgs_per_group);
 }
 
 // dx [B][H][W][Cin] from g_split [2][B][Ho][Wo][Cout]; image = mode-1 prepared weights [2][taps][Cin][Cout]
 extern "C" int rslo_conv2d_tc_backward_data(const float* g_split, int B, int H, int W, int Cin, const float* image_t, int Cout,
-                                            int ksize, int stride, float* dx, void* workspace, size_t workspace_bytes,
-                                            rslo_stream_t stream)
+                                            int ksize, int stride, float* dx, int accumulate, void* workspace,
+                                            size_t workspace_bytes, rslo_stream_t stream)
 {
     if (!rslo_conv2d_tc_supported(Cin, Cout, ksize, stride)) {
         set_last_error("rslo_conv2d_tc_backward_data: unsupported shape", cudaErrorInvalidValue);
@@ -734,14 +776,14 @@ extern "C" int rslo_conv2d_tc_backward_data(const float* g_split, int B, int H, 
         for (int ky = 0; ky < ksize; ++ky)
             for (int kx = 0; kx < ksize; ++kx) taps[n++] = ConvTap{0, pad - kx, 0, pad - ky, ky * ksize + kx};
         return run_conv(g_split, B, Ho, Wo, Cout, 1, image_t, ksize * ksize, Cin, H, W, taps, n, dx, H, W, 1, 0, 1, 0, Cin,
-                        nullptr, 0, workspace, workspace_bytes, st);
+                        nullptr, 0, workspace, workspace_bytes, st, nullptr, 1, accumulate);
     }
     if ((H & 1) || (W & 1)) {
         set_last_error("rslo_conv2d_tc_backward_data: stride 2 needs even H, W", cudaErrorInvalidValue);
         return (int)cudaErrorInvalidValue;
     }
     // 1x1 / stride 2: only the even-even class receives gradient, the rest of dx is zero
-    if (ksize == 1) RSLO_CHECK(cudaMemsetAsync(dx, 0, (size_t)B * H * W * Cin * 4, st));
+    if (ksize == 1 && !accumulate) RSLO_CHECK(cudaMemsetAsync(dx, 0, (size_t)B * H * W * Cin * 4, st));
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
             int n = 0;
@@ -756,7 +798,7 @@ extern "C" int rslo_conv2d_tc_backward_data(const float* g_split, int B, int H, 
             }
             if (n == 0) continue;
             const int rc = run_conv(g_split, B, Ho, Wo, Cout, 1, image_t, ksize * ksize, Cin, H / 2, W / 2, taps, n, dx, H, W, 2,
-                                    py, 2, px, Cin, nullptr, 0, workspace, workspace_bytes, st);
+                                    py, 2, px, Cin, nullptr, 0, workspace, workspace_bytes, st, nullptr, 1, accumulate);
             if (rc) return rc;
         }
     return 0;
@@ -770,8 +812,8 @@ extern "C" size_t rslo_conv2d_tc_wgrad_scratch_bytes(int Cin, int Cout, int ksiz
 // grad_weight_oihw [Cout][Cin][k][k] (= or += with accumulate) from x_split [2][B][H][W][Cin], g_split [2][B][Ho][Wo][Cout];
 // scratch: rslo_conv2d_tc_wgrad_scratch_bytes
 extern "C" int rslo_conv2d_tc_backward_weight(const float* x_split, const float* g_split, int B, int H, int W, int Cin, int Cout,
-                                              int ksize, int stride, float* scratch, int accumulate, float* grad_weight_oihw,
-                                              rslo_stream_t stream)
+                                              int ksize, int stride, int Cout_real, float* scratch, int accumulate,
+                                              float* grad_weight_oihw, rslo_stream_t stream)
 {
     if (!rslo_conv2d_tc_supported(Cin, Cout, ksize, stride) || (H % stride) || (W % stride)) {
         set_last_error("rslo_conv2d_tc_backward_weight: unsupported shape", cudaErrorInvalidValue);
@@ -813,15 +855,17 @@ extern "C" int rslo_conv2d_tc_backward_weight(const float* x_split, const float*
     if (rc) return rc;
     rc = encode_act(&tmG, g_split, B, Ho, Wo, Cout, 1, P.Wt, P.Ht, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    RSLO_CHECK(cudaMemsetAsync(scratch, 0, (size_t)P.ntaps * Cin * Cout * 4, st));
+    if (grad_weight_oihw != nullptr) RSLO_CHECK(cudaMemsetAsync(scratch, 0, (size_t)P.ntaps * Cin * Cout * 4, st));
     const dim3 grid(xs, gsets, ntiles);
     if (NT == 128) rc = launch_wgrad<128>(tmX, tmG, P, grid, scratch, st);
     else if (NT == 64) rc = launch_wgrad<64>(tmX, tmG, P, grid, scratch, st);
     else rc = launch_wgrad<32>(tmX, tmG, P, grid, scratch, st);
     if (rc) return rc;
-    const int total = P.ntaps * Cin * Cout;
+    if (grad_weight_oihw == nullptr) return 0;          // left in scratch for rslo_conv2d_multi_wgrad_finish
+    if (Cout_real <= 0 || Cout_real > Cout) Cout_real = Cout;
+    const int total = P.ntaps * Cin * Cout_real;
     RSLO_COUNT();
-    k_wgrad_finish<<<cdiv(total, 256), 256, 0, st>>>(scratch, Cout, Cin, P.ntaps, accumulate, grad_weight_oihw);
+    k_wgrad_finish<<<cdiv(total, 256), 256, 0, st>>>(scratch, Cout_real, Cout, Cin, P.ntaps, accumulate, grad_weight_oihw);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc_backward_weight(finish)");
     return 0;
 }

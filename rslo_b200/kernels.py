@@ -506,13 +506,15 @@ def conv2d_split(x_nhwc, out=None):
     return out
 
 
-def conv2d_tc_prepare(weight_oihw, mode, out=None):
-    """OIHW weight -> split image [2, k*k, N, Kd] (mode 0 forward: N=Cout, Kd=Cin; mode 1 data gradient)."""
+def conv2d_tc_prepare(weight_oihw, mode, out=None, cout_padded=None):
+    """OIHW weight -> split image [2, k*k, N, Kd] (mode 0 forward: N=Cout, Kd=Cin; mode 1 data gradient);
+    `cout_padded` zero-pads the output channels (narrow 7- / 1-channel heads -> 32)."""
     w = _f32(weight_oihw.detach().contiguous())
     cout, cin, ks, _ = w.shape
+    cp = cout if cout_padded is None else int(cout_padded)
     if out is None:
-        out = torch.empty(2 * ks * ks * cin * cout, dtype=torch.float32, device=w.device)
-    check(lib.rslo_conv2d_tc_prepare(ptr(w), cout, cin, ks, mode, ptr(out), stream()), "rslo_conv2d_tc_prepare")
+        out = torch.empty(2 * ks * ks * cin * cp, dtype=torch.float32, device=w.device)
+    check(lib.rslo_conv2d_tc_prepare(ptr(w), cout, cp, cin, ks, mode, ptr(out), stream()), "rslo_conv2d_tc_prepare")
     _count()
     return out
 
@@ -524,8 +526,9 @@ def _cost_conv2d(out, x_split, image, cout, ksize, stride, *a, **k):
 
 
 @_profiled("conv2d_tc", _cost_conv2d)
-def conv2d_tc_forward(x_split, image, cout, ksize, stride, bias=None, relu=False, out=None):
-    """y [B,Ho,Wo,Cout] = conv(x) (+bias)(ReLU); x_split [2,B,H,W,Cin]."""
+def conv2d_tc_forward(x_split, image, cout, ksize, stride, bias=None, relu=False, out=None, stats=None, imgs_per_group=1):
+    """y [B,Ho,Wo,Cout] = conv(x) (+bias)(ReLU); x_split [2,B,H,W,Cin].  `stats` (float64 [G,Cout,2], zeroed by
+    the caller) receives the per-group channel sums / sums of squares of y (BatchNorm batch statistics)."""
     x = _f32(x_split)
     _, B, H, W, cin = x.shape
     pad = ksize // 2
@@ -534,7 +537,8 @@ def conv2d_tc_forward(x_split, image, cout, ksize, stride, bias=None, relu=False
         out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x.device)
     ws = _conv_ws()
     check(lib.rslo_conv2d_tc_forward(ptr(x), B, H, W, cin, ptr(image), cout, ksize, stride, ptr(bias), 1 if relu else 0,
-                                     ptr(out), ptr(ws), ws.numel(), stream()), "rslo_conv2d_tc_forward")
+                                     ptr(out), ptr(stats), imgs_per_group, ptr(ws), ws.numel(), stream()),
+          "rslo_conv2d_tc_forward")
     _count()
     return out
 
@@ -546,16 +550,18 @@ def _cost_conv2d_bwd(out, g_split, image_t, in_shape, ksize, stride, *a, **k):
 
 
 @_profiled("conv2d_tc_dgrad", _cost_conv2d_bwd)
-def conv2d_tc_backward_data(g_split, image_t, in_shape, ksize, stride, out=None):
-    """dx [B,H,W,Cin] from g_split [2,B,Ho,Wo,Cout] and the mode-1 weight image."""
+def conv2d_tc_backward_data(g_split, image_t, in_shape, ksize, stride, out=None, accumulate=False):
+    """dx [B,H,W,Cin] (= or +=) from g_split [2,B,Ho,Wo,Cout] and the mode-1 weight image."""
     g = _f32(g_split)
     B, H, W, cin = in_shape
     cout = g.shape[-1]
     if out is None:
+        assert not accumulate
         out = torch.empty((B, H, W, cin), dtype=torch.float32, device=g.device)
     ws = _conv_ws()
-    check(lib.rslo_conv2d_tc_backward_data(ptr(g), B, H, W, cin, ptr(image_t), cout, ksize, stride, ptr(out), ptr(ws),
-                                           ws.numel(), stream()), "rslo_conv2d_tc_backward_data")
+    check(lib.rslo_conv2d_tc_backward_data(ptr(g), B, H, W, cin, ptr(image_t), cout, ksize, stride, ptr(out),
+                                           1 if accumulate else 0, ptr(ws), ws.numel(), stream()),
+          "rslo_conv2d_tc_backward_data")
     _count()
     return out
 
@@ -567,17 +573,92 @@ def _cost_conv2d_wgrad(out, x_split, g_split, ksize, stride, *a, **k):
 
 
 @_profiled("conv2d_tc_wgrad", _cost_conv2d_wgrad)
-def conv2d_tc_backward_weight(x_split, g_split, ksize, stride, out=None, accumulate=False):
-    """grad_weight OIHW [Cout,Cin,k,k] from x_split [2,B,H,W,Cin] and g_split [2,B,Ho,Wo,Cout]."""
+def conv2d_tc_backward_weight(x_split, g_split, ksize, stride, out=None, accumulate=False, cout_real=None, scratch=None):
+    """grad_weight OIHW [Cout,Cin,k,k] from x_split [2,B,H,W,Cin] and g_split [2,B,Ho,Wo,Cout].
+    `scratch` given (zeroed float32 [k*k*Cin*Cout]): the products are added into it as [k*k][Cin][Cout] and left
+    there (no OIHW output; see conv2d_multi_wgrad_finish)."""
     x, g = _f32(x_split), _f32(g_split)
     _, B, H, W, cin = x.shape
     cout = g.shape[-1]
-    if out is None:
-        assert not accumulate
-        out = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
-    scratch = workspace(lib.rslo_conv2d_tc_wgrad_scratch_bytes(cin, cout, ksize), "conv2d_wgrad")
-    check(lib.rslo_conv2d_tc_backward_weight(ptr(x), ptr(g), B, H, W, cin, cout, ksize, stride, ptr(scratch),
+    cr = cout if cout_real is None else int(cout_real)
+    deferred = scratch is not None
+    if deferred:
+        out = None
+    else:
+        if out is None:
+            assert not accumulate
+            out = torch.empty((cr, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+        scratch = workspace(lib.rslo_conv2d_tc_wgrad_scratch_bytes(cin, cout, ksize), "conv2d_wgrad")
+    check(lib.rslo_conv2d_tc_backward_weight(ptr(x), ptr(g), B, H, W, cin, cout, ksize, stride, cr, ptr(scratch),
                                              1 if accumulate else 0, ptr(out), stream()),
           "rslo_conv2d_tc_backward_weight")
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: the head between its convolutions (csrc/head_ops.cu) — thin pointer-passing wrappers; the buffers are
+# owned by rslo_b200/layers/head_tc.py
+# ------------------------------------------------------------------------------------------------
+def conv2d_multi_prepare(table_dev, n):
+    check(lib.rslo_conv2d_multi_prepare(ptr(table_dev), n, stream()), "rslo_conv2d_multi_prepare")
+    _count()
+
+
+def conv2d_multi_wgrad_finish(table_dev, n):
+    check(lib.rslo_conv2d_multi_wgrad_finish(ptr(table_dev), n, stream()), "rslo_conv2d_multi_wgrad_finish")
+    _count()
+
+
+def head_pack_input(x1, x2, split_out, mask_out):
+    """x1, x2 [B,C,H,W] (NCHW) -> split pair [2,B,H,W,2C] of cat(x1,x2) and mask [B,H,W] = (sum_c x1 != 0)."""
+    x1, x2 = _f32(x1), _f32(x2)
+    B, Cc, H, W = x1.shape
+    check(lib.rslo_head_pack_input(ptr(x1), ptr(x2), B, Cc, H * W, ptr(split_out), ptr(mask_out), stream()),
+          "rslo_head_pack_input")
+    _count()
+
+
+def head_unpack_grad(dx, g1, g2):
+    """dx [B,H,W,2C] -> g1, g2 [B,C,H,W]."""
+    B, Cc, H, W = g1.shape
+    check(lib.rslo_head_unpack_grad(ptr(dx), B, Cc, H * W, ptr(g1), ptr(g2), stream()), "rslo_head_unpack_grad")
+    _count()
+
+
+def bn_act_forward(y, ipg, stats, gamma, beta, running_mean, running_var, nbt, eps, momentum, update_repeat,
+                   residual, relu, z, z_split, mean_rstd):
+    B, H, W, Cc = y.shape
+    check(lib.rslo_bn_act_forward(ptr(y), B, H * W, Cc, ipg, ptr(stats), ptr(gamma), ptr(beta), ptr(running_mean),
+                                  ptr(running_var), ptr(nbt), float(eps), float(momentum), int(update_repeat),
+                                  ptr(residual), 1 if relu else 0, ptr(z), ptr(z_split), ptr(mean_rstd), stream()),
+          "rslo_bn_act_forward")
+    _count()
+
+
+def bn_act_backward(dz, z, y, ipg, mean_rstd, gamma, relu, batch_stats, sums, g_split, dres, dres_accumulate, dgamma,
+                    dbeta, dbias):
+    B, H, W, Cc = y.shape
+    check(lib.rslo_bn_act_backward(ptr(dz), ptr(z), ptr(y), B, H * W, Cc, ipg, ptr(mean_rstd), ptr(gamma),
+                                   1 if relu else 0, 1 if batch_stats else 0, ptr(sums), ptr(g_split), ptr(dres),
+                                   1 if dres_accumulate else 0, ptr(dgamma), ptr(dbeta), ptr(dbias), stream()),
+          "rslo_bn_act_backward")
+    _count(2)
+
+
+def upcat_split(z, up, ld, choff, dst_split):
+    B, H, W, Cc = z.shape
+    check(lib.rslo_upcat_split(ptr(z), B, H, W, Cc, up, ld, choff, ptr(dst_split), stream()), "rslo_upcat_split")
+    _count()
+
+
+def upcat_backward(dcat, shape, up, ld, choff, dz, accumulate):
+    B, H, W, Cc = shape
+    check(lib.rslo_upcat_backward(ptr(dcat), B, H, W, Cc, up, ld, choff, ptr(dz), 1 if accumulate else 0, stream()),
+          "rslo_upcat_backward")
+    _count()
+
+
+def bias_grad(g, n_rows, ld, c, out):
+    check(lib.rslo_bias_grad(ptr(g), n_rows, ld, c, ptr(out), stream()), "rslo_bias_grad")
+    _count()

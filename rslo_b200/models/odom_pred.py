@@ -8,7 +8,8 @@ entries, tests/golden/state_dict_shapes.json).  Differences that do not change a
   * the T=1 and T=20 confidences share one pass of the confidence conv stack (the reference runs the
     stack twice on the same values, `odom_pred.py:242-258`);
   * cell-anchor grids are cached instead of rebuilt per call.
-The 2-D convolutions are dense contractions and run through cuDNN in FP32.
+The trunk (every convolution, BatchNorm, ReLU, residual add, upsample + concat) runs on the repo's own kernels:
+layers/head_tc.py over csrc/conv2d_tc.cu (tcgen05 split-TF32 implicit GEMM) and csrc/head_ops.cu.
 """
 import os
 
@@ -20,6 +21,7 @@ from ..data.dataset import from_pointwise_local_transformation_tch
 from ..layers.common import ParameterLayer
 from ..layers.confidence import ConfidenceModule
 from ..layers.conv2d_tc import Conv2dTC
+from ..layers.head_tc import HeadTrunkEngine, head_trunk
 from ..layers.MaskConv import MaskConv
 from ..layers.SparseConv import SPC_BN2d, SPC_ReLU, SPC_SyncBN2d
 from ..torchplus import Empty, change_default_args
@@ -30,6 +32,9 @@ REGISTERED_ODOM_PRED_CLASSES = {}
 # The 2-D convolutions run in true FP32: cuDNN's default TF32 path gives ~1e-3 pose error, outside the
 # 1e-4 relative parity bound of the path (measured on B200, tests/test_gpu_pair.py).
 HEAD_ALLOW_TF32 = False
+# The trunk runs on the repo's own tcgen05 convolutions + fused BN/ReLU kernels (layers/head_tc.py).
+# RSLO_HEAD_TC=0 switches to torch/cuDNN FP32 for A/B comparison only.
+USE_OWN_TRUNK = os.environ.get("RSLO_HEAD_TC", "1") != "0"
 # cuDNN autotuning of the head's FP32 convolutions (shapes are static; tuned once before graph capture).
 HEAD_CUDNN_BENCHMARK = os.environ.get("RSLO_CUDNN_BENCHMARK", "1") != "0"
 
@@ -86,13 +91,14 @@ class _FlatHead(nn.Module):
     """Tensor-in / tensor-out view of the head for CUDA-graph capture (shares the head's parameters;
     never registered as a child, so state_dict keys are unchanged)."""
 
-    def __init__(self, head, n_levels):
+    def __init__(self, head, n_levels, imgs_per_group):
         super().__init__()
         self.head = head
         self.n_levels = n_levels
+        self.imgs_per_group = imgs_per_group
 
     def forward(self, *bevs):
-        d = self.head._forward(list(bevs))
+        d = self.head._forward(list(bevs), imgs_per_group=self.imgs_per_group)
         out = [d["translation_preds"][0], d["rotation_preds"][0], d["tq_map_g"], d["t_conf"], d["r_conf"]]
         for pred, mask in d["pyramid_motion"]:
             out += [pred, mask]
@@ -221,27 +227,44 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
         return [torch.stack(x1, dim=1).reshape(-1, C, H, W), torch.stack(x2, dim=1).reshape(-1, C, H, W)]
 
     def forward(self, xs, tq_map_gt=None, local_spatial_features=None, **kwargs):
+        """xs: the T frames' BEV maps, each [S,C,H,W] (S samples; the reference always has S = 1).  All ordered
+        frame pairs i<j of every sample go through the head in one pass; BatchNorm batch statistics are per sample."""
         if not isinstance(xs, list):
             xs = [xs]
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=HEAD_ALLOW_TF32, benchmark=HEAD_CUDNN_BENCHMARK):
-            if self.use_cuda_graph and xs[0].is_cuda and self.dense_predict and self.pred_pyramid_motion:
-                return self._forward_graphed(xs)
-            return self._forward(xs, tq_map_gt, local_spatial_features, **kwargs)
+        ipg = len(xs) * (len(xs) - 1) // 2 if self._cycle_constraint else 1
+        if self.use_cuda_graph and xs[0].is_cuda and self.dense_predict and self.pred_pyramid_motion:
+            return self._forward_graphed(xs, ipg)
+        return self._forward(xs, tq_map_gt, local_spatial_features, imgs_per_group=ipg, **kwargs)
 
     # ---- CUDA-graph replay of the head -----------------------------------------------------------
     # Every shape in the head is fixed by the BEV grid, so forward and backward are each captured
     # once per (frames, mode) into a CUDA graph (torch.cuda.make_graphed_callables) and replayed:
-    # ~2000 small cuDNN / elementwise launches per step become two graph launches.
+    # the ~450 kernel launches of a trunk pass and the tail's elementwise launches become two graph launches.
     use_cuda_graph = os.environ.get("RSLO_CUDA_GRAPHS", "1") != "0"
 
-    def _forward_graphed(self, xs):
+    def _apply(self, fn, *a, **k):
+        # parameters may move (net.to(device)): captured graphs and prepared weight images point at the old storage
+        self.__dict__.pop("_graphed", None)
+        e = self.__dict__.get("_trunk_engine")
+        if e is not None:
+            e.clear()
+        return super()._apply(fn, *a, **k)
+
+    def _mode_signature(self):
+        """what a captured graph bakes in besides shapes: per-layer BN mode (freeze_bn flips single layers to eval)
+        and which parameters receive gradients (freeze_bn_affine)"""
+        bn = tuple(m.training for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm))
+        rg = tuple(p.requires_grad for p in self.parameters())
+        return hash((bn, rg))
+
+    def _forward_graphed(self, xs, ipg):
         # one captured graph per stream: replays on different streams must not share static buffers
-        key = (len(xs), self.training, tuple(x.requires_grad for x in xs), tuple(xs[0].shape), xs[0].device.index,
-               torch.cuda.current_stream().cuda_stream)
+        key = (len(xs), self.training, self._mode_signature(), tuple(x.requires_grad for x in xs), tuple(xs[0].shape),
+               xs[0].device.index, torch.cuda.current_stream().cuda_stream, torch.is_grad_enabled())
         cache = self.__dict__.setdefault("_graphed", {})
         g = cache.get(key)
         if g is None:
-            flat = _FlatHead(self, len(self.deblocks))
+            flat = _FlatHead(self, len(self.deblocks), ipg)
             flat.training = self.training
             bufs = {n: b.clone() for n, b in self.named_buffers()}
             sample = tuple(torch.randn_like(x).requires_grad_(x.requires_grad) for x in xs)
@@ -257,20 +280,57 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
         return {"translation_preds": [t], "rotation_preds": [q], "tq_map_g": tq_map_g, "pyramid_motion": pyramid,
                 "transformed_inputs": None, "t_conf": t_conf, "r_conf": r_conf}
 
-    def _forward(self, xs, tq_map_gt=None, local_spatial_features=None, **kwargs):
-        if not isinstance(xs, list):
-            xs = [xs]
-        if self._cycle_constraint:
-            xs = self.create_cycle_constraint_data(xs)
-        input_mask_bool = (torch.sum(xs[0], dim=1, keepdim=True) != 0).detach_()
-        input_mask = input_mask_bool.to(dtype=xs[0].dtype)
-        x = torch.cat(xs, dim=1)
+    # ---- trunk: BEV pair -> raw (t,q) map, confidence logits, pyramid predictions -------------------------
+    def _engine(self):
+        e = self.__dict__.get("_trunk_engine")
+        if e is None:
+            e = self.__dict__["_trunk_engine"] = HeadTrunkEngine(self)
+        return e
+
+    def _trunk_own(self, x1, x2, imgs_per_group):
+        """csrc/conv2d_tc.cu + csrc/head_ops.cu (layers/head_tc.py): NHWC, split-TF32 tcgen05 convolutions."""
+        outs = head_trunk(self._engine(), x1, x2, imgs_per_group or x1.shape[0])
+        tq32, tl32, rl32, mask = outs[0], outs[1], outs[2], outs[-1]
+        nchw = lambda t, c: t[..., :c].permute(0, 3, 1, 2)
+        return nchw(tq32, 7), nchw(tl32, 1), nchw(rl32, 1), [nchw(p, 7) for p in outs[3:-1]], mask.unsqueeze(1)
+
+    def _trunk_torch(self, x1, x2):
+        """The same trunk through torch / cuDNN FP32 (A/B switch RSLO_HEAD_TC=0; never the default)."""
+        input_mask = (torch.sum(x1, dim=1, keepdim=True) != 0).detach_().to(dtype=x1.dtype)
+        x = torch.cat([x1, x2], dim=1)
         ups = []
         for i in range(len(self.blocks)):
             x = self.blocks[i](x)
             ups.append(self.skip_blocks[i](x[0]))
         x = x[0]
-        x_middle = x
+        py_raw = []
+        for i in range(len(self.deblocks)):
+            x = torch.cat([x, ups[-(i + 1)]], dim=1)
+            x = self.deblocks[i](x)
+            if self.pred_pyramid_motion and i < len(self.deblocks) - 1:
+                py_raw.append(self.pyramid_motion_blocks[i](x))
+        tq_map = self.tq_map_conv(x)
+        t_logit = self.t_map_conf.conf_model(x)
+        r_logit = self.q_map_conf.conf_model(x)
+        if self.training:                   # second scoring pass of the reference (`odom_pred.py:242-258`): same
+            with torch.no_grad():           # values, but the BN running statistics move a second time
+                self.t_map_conf.conf_model(x)
+                self.q_map_conf.conf_model(x)
+        return tq_map, t_logit, r_logit, py_raw, input_mask
+
+    def _forward(self, xs, tq_map_gt=None, local_spatial_features=None, imgs_per_group=None, **kwargs):
+        if not isinstance(xs, list):
+            xs = [xs]
+        assert self.dense_predict, "only the dense-prediction head is built (shipped configs)"
+        if self._cycle_constraint:
+            xs = self.create_cycle_constraint_data(xs)
+        x1, x2 = xs
+        if USE_OWN_TRUNK and x1.is_cuda:
+            tq_map, t_logit, r_logit, py_raw, input_mask = self._trunk_own(x1, x2, imgs_per_group)
+        else:
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=HEAD_ALLOW_TF32, benchmark=HEAD_CUDNN_BENCHMARK):
+                tq_map, t_logit, r_logit, py_raw, input_mask = self._trunk_torch(x1, x2)
+
         py_masks = []
         if self.pred_pyramid_motion:
             p_mask = input_mask
@@ -278,39 +338,20 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
                 p_mask = self.mask_gen_pools[-(i + 1)](p_mask)
                 py_masks.append(p_mask)
             py_masks.reverse()
-        py_preds = []
-        for i in range(len(self.deblocks)):
-            x = torch.cat([x, ups[-(i + 1)]], dim=1)
-            x = self.deblocks[i](x)
-            if self.pred_pyramid_motion and i < len(self.deblocks) - 1:
-                py_pred = self.pyramid_motion_blocks[i](x)
-                py_preds.append([py_pred * (py_masks[i] > 0).to(dtype=py_pred.dtype), py_masks[i]])
-        x_tail = x
-        tq_map = self.tq_map_conv(x)
+        py_preds = [[p * (m > 0).to(dtype=p.dtype), m] for p, m in zip(py_raw, py_masks)]
         q_map = tq_map[:, 3:] / torch.norm(tq_map[:, 3:], dim=1, keepdim=True)
         tq_map = torch.cat([tq_map[:, :3], q_map], dim=1)
 
-        odoms = []
-        tq_map_g = tq_map
-        t_conf = torch.ones_like(tq_map[:, :1])
-        r_conf = torch.ones_like(tq_map[:, :1])
-        if self.dense_predict:
-            t_conf, t_logit = self.t_map_conf(x_tail, extra_mask=input_mask, return_logit=True)
-            r_conf, r_logit = self.q_map_conf(x_tail, extra_mask=input_mask, return_logit=True)
-            tq_map_g = from_pointwise_local_transformation_tch(tq_map, self.point_cloud_range)
-            odoms += self.aggregate_tq([tq_map_g], t_confs=[t_conf], r_confs=[r_conf])
-            temp_t_conf = self.t_map_conf(None, extra_mask=input_mask, temperature=20, logit=t_logit.detach())
-            temp_r_conf = self.q_map_conf(None, extra_mask=input_mask, temperature=20, logit=r_logit.detach())
-            temp_tq_conf = torch.cat([temp_t_conf, temp_r_conf], dim=1).detach()
-            pyramid_motion = py_preds + [[tq_map * input_mask, input_mask * temp_tq_conf]]
-            for p in range(2, len(pyramid_motion) + 1):
-                pyramid_motion[-p][1] = pyramid_motion[-p][1] * self.hier_weight_gen(pyramid_motion[-(p - 1)][1])
-        else:
-            pyramid_motion = []
-            x = self.pool(x_middle)
-            x = self.fc1(x.view(x.size(0), -1))
-            x = self.fc2(self.odom_dropout(F.relu(x)))
-            odoms += [x]
+        t_conf = self.t_map_conf(None, extra_mask=input_mask, logit=t_logit)
+        r_conf = self.q_map_conf(None, extra_mask=input_mask, logit=r_logit)
+        tq_map_g = from_pointwise_local_transformation_tch(tq_map, self.point_cloud_range)
+        odoms = self.aggregate_tq([tq_map_g], t_confs=[t_conf], r_confs=[r_conf])
+        temp_t_conf = self.t_map_conf(None, extra_mask=input_mask, temperature=20, logit=t_logit.detach())
+        temp_r_conf = self.q_map_conf(None, extra_mask=input_mask, temperature=20, logit=r_logit.detach())
+        temp_tq_conf = torch.cat([temp_t_conf, temp_r_conf], dim=1).detach()
+        pyramid_motion = py_preds + [[tq_map * input_mask, input_mask * temp_tq_conf]]
+        for p in range(2, len(pyramid_motion) + 1):
+            pyramid_motion[-p][1] = pyramid_motion[-p][1] * self.hier_weight_gen(pyramid_motion[-(p - 1)][1])
 
         translations, rotations = [], []
         for x in odoms:

@@ -164,30 +164,3 @@ def test_bench_reference_arm_rank_nonzero_exits_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        env=dict(os.environ, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
-
-
-@pytest.mark.parametrize("ks,st,B", [(3, 1, 2), (3, 2, 1), (1, 2, 1)])
-def test_conv2d_grid_tables_reproduce_conv2d(ks, st, B):
-    """The static neighbour tables behind Conv2dTC (rslo_b200/layers/conv2d_tc.py): a gather-conv over them
-    (oracle's CPU gather_conv) equals F.conv2d, and the transposed table reproduces the input gradient."""
-    from oracle.sparse import gather_conv
-    from rslo_b200.layers.conv2d_tc import grid_tables
-    g = torch.Generator().manual_seed(ks * 10 + st)
-    cin, cout, H, W = 5, 4, 9, 12
-    pad = ks // 2
-    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
-    w = torch.randn(cout, cin, ks, ks, generator=g, dtype=torch.float64)
-    nbr, nbr_t, mirror, Ho, Wo = grid_tables(B, H, W, ks, st, pad, torch.device("cpu"))
-    y = torch.nn.functional.conv2d(x, w, None, st, pad)
-    assert (Ho, Wo) == tuple(y.shape[2:])
-    rows = x.detach().permute(0, 2, 3, 1).reshape(-1, cin)
-    w9 = w.permute(2, 3, 1, 0).reshape(ks * ks, cin, cout)
-    y_rows = gather_conv(rows, nbr, w9)
-    assert torch.allclose(y_rows, y.permute(0, 2, 3, 1).reshape(-1, cout), atol=1e-12)
-    go = torch.randn(y.shape, generator=g, dtype=torch.float64)
-    y.backward(go)
-    g_rows = go.permute(0, 2, 3, 1).reshape(-1, cout)
-    K_ = ks * ks
-    wt = torch.stack([w9[K_ - 1 - k if mirror else k].t() for k in range(K_)])       # [K, Cout, Cin]
-    gx_rows = gather_conv(g_rows, nbr_t, wt)
-    assert torch.allclose(gx_rows, x.grad.permute(0, 2, 3, 1).reshape(-1, cin), atol=1e-12)

@@ -398,33 +398,45 @@ def test_stress_grid_voxelize_and_rulebook_bit_exact(K):
 @pytest.mark.parametrize("cin,cout,h,w,ks,st,B", [(256, 128, 24, 44, 3, 2, 1), (128, 128, 24, 22, 3, 1, 2),
                                                   (512, 128, 12, 22, 3, 1, 1), (192, 64, 48, 44, 3, 1, 1),
                                                   (64, 32, 48, 88, 3, 1, 1), (256, 128, 24, 44, 1, 2, 1),
-                                                  (256, 256, 12, 22, 3, 1, 3)])
+                                                  (256, 256, 12, 22, 3, 1, 3), (32, 7, 24, 44, 1, 1, 2),
+                                                  (128, 256, 24, 44, 3, 2, 2), (64, 1, 16, 24, 1, 1, 1)])
 def test_conv2d_tensor_core_matches_fp64(cuda, cin, cout, h, w, ks, st, B):
-    """Head convolution on the tensor-core gather-GEMM (channels_last rows + static neighbour table):
-    forward, data gradient (TC) and weight gradient (cuDNN) against float64 autograd."""
-    from rslo_b200.layers import conv2d_tc
-    from rslo_b200.layers.conv2d_tc import Conv2dTC
-    monkey = conv2d_tc.USE_TC
-    conv2d_tc.USE_TC = True
+    """Head convolutions (csrc/conv2d_tc.cu: TMA-staged split-TF32 tcgen05 implicit GEMM) through the C ABI:
+    forward (+bias, + fused BatchNorm statistics), data gradient (store and accumulate) and weight gradient
+    against float64 autograd.  Narrow heads (7 / 1 output channels) run zero-padded to 32."""
+    from rslo_b200 import kernels as K
     g = torch.Generator().manual_seed(cin + cout + h)
-    conv = Conv2dTC(cin, cout, ks, stride=st, padding=ks // 2, bias=True).cuda()
-    with torch.no_grad():
-        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (cin * ks * ks)) ** 0.5)
-        conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
-    x = torch.randn(B, cin, h, w, generator=g).cuda().requires_grad_(True)
-    y = conv(x)
-    go = torch.randn(y.shape, generator=g).cuda()
-    y.backward(go)
-    xd = x.detach().double().requires_grad_(True)
-    wd = conv.weight.detach().double().requires_grad_(True)
-    bd = conv.bias.detach().double().requires_grad_(True)
-    yd = torch.nn.functional.conv2d(xd, wd, bd, st, ks // 2)
-    yd.backward(go.double())
+    wt = (torch.randn(cout, cin, ks, ks, generator=g) * (2.0 / (cin * ks * ks)) ** 0.5).cuda()
+    bias = (torch.randn(cout, generator=g) * 0.1).cuda()
+    x = torch.randn(B, h, w, cin, generator=g).cuda()
+    coutp = (cout + 31) // 32 * 32
+    bias_p = torch.zeros(coutp, device="cuda")
+    bias_p[:cout] = bias
+    xs = K.conv2d_split(x)
+    stats = torch.zeros(B, coutp, 2, dtype=torch.float64, device="cuda")
+    y = K.conv2d_tc_forward(xs, K.conv2d_tc_prepare(wt, 0, cout_padded=coutp), coutp, ks, st, bias=bias_p, stats=stats,
+                            imgs_per_group=1)
+    xd = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+    wd = wt.double().requires_grad_(True)
+    yd = torch.nn.functional.conv2d(xd, wd, bias.double(), st, ks // 2)
+    go = torch.zeros(y.shape, device="cuda")
+    go[..., :cout] = torch.randn(y.shape[:3] + (cout,), generator=g).cuda()
+    yd.backward(go[..., :cout].permute(0, 3, 1, 2).double())
+
     def rel(a, b):
         return float((a.double() - b).abs().max() / b.abs().max())
-    assert y.shape == yd.shape
-    assert rel(y, yd) < 5e-6
-    assert rel(x.grad, xd.grad) < 5e-6
-    assert rel(conv.weight.grad, wd.grad) < 1e-4          # cuDNN FP32 weight gradient
-    assert rel(conv.bias.grad, bd.grad) < 1e-5
-    conv2d_tc.USE_TC = monkey
+    assert rel(y[..., :cout], yd.permute(0, 2, 3, 1)) < 5e-6
+    if coutp != cout:
+        assert float(y[..., cout:].abs().max()) == 0.0
+    ref_stats = torch.stack([yd.sum(dim=(2, 3)), (yd * yd).sum(dim=(2, 3))], dim=-1)
+    assert rel(stats[:, :cout], ref_stats) < 1e-5
+    gs = K.conv2d_split(go)
+    img_t = K.conv2d_tc_prepare(wt, 1, cout_padded=coutp)
+    dx = K.conv2d_tc_backward_data(gs, img_t, (B, h, w, cin), ks, st)
+    assert rel(dx, xd.grad.permute(0, 2, 3, 1)) < 5e-6
+    base = torch.randn(dx.shape, generator=g).cuda()
+    acc = base.clone()
+    K.conv2d_tc_backward_data(gs, img_t, (B, h, w, cin), ks, st, out=acc, accumulate=True)
+    assert rel(acc - base, xd.grad.permute(0, 2, 3, 1)) < 5e-6
+    dw = K.conv2d_tc_backward_weight(xs, gs, ks, st, cout_real=cout)
+    assert dw.shape == wt.shape and rel(dw, wd.grad) < 5e-6
