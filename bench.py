@@ -244,43 +244,45 @@ def main():
     PREFETCH_DEPTH = 1                       # examples prepared ahead (2 measured no faster, and slower from host)
     prefetch = {}                            # (pair index, from_host) -> prepared example
 
-    def prepared_example(idx, from_host):
-        """net.prepare(): voxelisation + index tables on a side stream (the reference does its voxelisation
-        ahead of time in DataLoader workers).  From host: the pinned scans are copied inside prepare()."""
-        a, b = (host if from_host else resident)[idx % pool_n]
-        if from_host:
-            h2d_bytes[0] += a.numel() * 4 + b.numel() * 4
-        return net.prepare({"points": [a, b], "host_outputs": False})
+    def prepared_step(i, from_host):
+        """net.prepare(): voxelisation + index tables of ALL samples of step i on a side stream (the reference does
+        its voxelisation ahead of time in DataLoader workers).  From host: the pinned scans are copied inside prepare()."""
+        src = host if from_host else resident
+        pts = []
+        for j in range(ppg):
+            a, b = src[(i * ppg + j) % pool_n]
+            pts += [a, b]
+            if from_host:
+                h2d_bytes[0] += a.numel() * 4 + b.numel() * 4
+        return net.prepare({"points": pts, "n_samples": ppg, "host_outputs": False})
 
     def step(i, from_host):
+        """one step = the ppg samples of the batch through ONE net(example) call (example["n_samples"] = ppg):
+        loss = mean over the samples; one backward"""
         if train:
             reducer.zero_()
             for c in image_caches:          # a real training step changes the weights: rebuild the split-TF32
                 c._c.clear()                # weight images once per step, as an optimizer step would force
-        outs = []
-        for j in range(ppg):
-            idx = i * ppg + j
-            ex = prefetch.pop((idx, from_host), None)
-            if ex is None:
-                ex = prepared_example(idx, from_host)
-            if train:
+        ex = prefetch.pop((i, from_host), None)
+        if ex is None:
+            ex = prepared_step(i, from_host)
+        if train:
+            ret = net(ex)
+            ret["loss"].sum().backward()
+            res = ret["loss"].detach().reshape(-1)
+        else:
+            with torch.no_grad():
                 ret = net(ex)
-                (ret["loss"].sum() / ppg).backward()
-                outs.append(ret["loss"].detach())
-            else:
-                with torch.no_grad():
-                    ret = net(ex)
-                outs.append(torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1))
-            # the following pairs are prepared while this one's kernels run (the preparation's only host wait
-            # then happens with at least one whole pair still queued on the main stream)
-            for stale in [k for k in prefetch if k[1] != from_host or k[0] <= idx]:
-                del prefetch[stale]
-            for ahead in range(1, PREFETCH_DEPTH + 1):
-                if (idx + ahead, from_host) not in prefetch:
-                    prefetch[(idx + ahead, from_host)] = prepared_example(idx + ahead, from_host)
+            res = torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1).reshape(-1)
+        # the next step's samples are prepared while this one's kernels run (the preparation's only host wait
+        # then happens with a whole step still queued on the main stream)
+        for stale in [k for k in prefetch if k[1] != from_host or k[0] <= i]:
+            del prefetch[stale]
+        for ahead in range(1, PREFETCH_DEPTH + 1):
+            if (i + ahead, from_host) not in prefetch:
+                prefetch[(i + ahead, from_host)] = prepared_step(i + ahead, from_host)
         if train:
             reducer.all_reduce()                    # pack into the flat buffer (+ NCCL all-reduce when N > 1)
-        res = torch.cat([o.reshape(-1) for o in outs])
         if from_host:
             r = res.cpu()                                                  # D2H of the step's result
             d2h_bytes[0] += r.numel() * 4
@@ -331,7 +333,7 @@ def main():
     h2d_bytes[0] = d2h_bytes[0] = 0
     ms_e2e = timed(args.steps, True, W)
     e2e = {"value": world * ppg * args.steps / (ms_e2e / 1e3), "unit": "pairs/s",
-           "h2d_bytes_per_step": h2d_bytes[0] // (args.steps * ppg + PREFETCH_DEPTH) * ppg, "d2h_bytes_per_step": d2h_bytes[0] // args.steps,
+           "h2d_bytes_per_step": h2d_bytes[0] // (args.steps + PREFETCH_DEPTH), "d2h_bytes_per_step": d2h_bytes[0] // args.steps,
            "ms_per_step": ms_e2e / args.steps}
 
     # roofline of the dominant kernel: profiled replica of the timed steps

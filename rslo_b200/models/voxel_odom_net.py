@@ -6,6 +6,11 @@
   * B200-native: ``example["points"][t]`` = raw scan ``[P,7]`` on the device; the fused
     scatter-voxeliser + VFE kernel (csrc/voxelize.cu) runs inside forward and also hands its site
     table to the sparse encoder, so the 11 MB/frame `voxels` tensor is never materialised.
+Several independent samples of a step go through ONE call: ``example["n_samples"] = S`` with the S*T frames
+listed sample-major.  Every sparse layer then launches once on all S*T frames, the head sees all S*pairs BEV pairs
+in one pass (BatchNorm batch statistics stay per sample / per frame exactly as in S separate calls, running
+statistics advance sample after sample) and ``loss`` is the mean over the samples, i.e. what S calls with gradient
+accumulation of loss/S produce (the reference itself asserts batch_size == 1, `middle.py:221`).
 """
 import time
 
@@ -280,11 +285,20 @@ class UnVoxelOdomNetICP3(nn.Module):
                 spatial_features.append(ret)
                 middle_conf_preds.append(conf_pred)
         self.end_timer("middle forward")
-        preds_dict = self.odom_predictor(spatial_features, tq_map_gt=None)
+        S = int(example.get("n_samples", 1))
+        T = len(spatial_features) // S
+        assert S * T == len(spatial_features), "n_samples must divide the number of frames"
+        if S == 1:
+            head_in = spatial_features
+        else:       # frame slot t of every sample -> one [S,C,H,W] batch: all pairs of all samples in one head pass
+            head_in = [torch.cat([spatial_features[s * T + t] for s in range(S)], dim=0) for t in range(T)]
+        preds_dict = self.odom_predictor(head_in, tq_map_gt=None)
         if self.training or self.testing:
             with torch.no_grad():
-                preds_dict["feature_mask"] = (torch.sum(torch.cat(spatial_features, dim=1), dim=1, keepdim=True) != 0).float()
-                disp = [torch.mean(s.detach(), dim=1, keepdim=True) for s in spatial_features]
+                preds_dict["feature_mask"] = torch.cat(
+                    [(torch.sum(torch.cat(spatial_features[s * T:(s + 1) * T], dim=1), dim=1, keepdim=True) != 0).float()
+                     for s in range(S)], dim=0)
+                disp = [torch.mean(sf.detach(), dim=1, keepdim=True) for sf in spatial_features]
                 preds_dict["middle_feature"] = [(d - torch.min(d)) / (torch.max(d) - torch.min(d) + 1e-12) for d in disp]
         preds_dict["middle_conf_preds"] = middle_conf_preds
         preds_dict["voxel_features"] = voxel_features
@@ -405,40 +419,52 @@ class UnVoxelOdomNetICP3(nn.Module):
         if consistency_loss is not None:
             assert len(preds_dict["middle_conf_preds"]) > 0
             feats = preds_dict["voxel_features"]
+            S = int(example.get("n_samples", 1))
+            T = len(feats) // S
+            n_pairs = T * (T - 1) // 2
             cols = [0, 1, 2, 4, 5, 6] if feats[0].shape[1] > 6 else [0, 1, 2, 3, 4, 5]
-            points = [[p[:, cols][None]] for p in feats]
-            point_confs = [p[None] for p in preds_dict["middle_conf_preds"]]
-            min_len = min(p[0].shape[1] for p in points)                   # voxel_odom_net.py:646-651
-            points = [[p[0][:, :min_len]] for p in points]
-            point_confs = create_cycle_constraint_data([p[:, :min_len] for p in point_confs])
-            new_points = []
-            for h, _ in enumerate(points[0]):
-                new_points.append(create_cycle_constraint_data([points[t][h] for t in range(len(points))], 1))
-            if len(new_points) < len(rotation_preds):
-                new_points = new_points + [new_points[-1]] * (len(rotation_preds) - len(new_points))
-            else:
-                new_points = new_points[:len(rotation_preds)]
             weights = [0.01, 0.01, 0.05, 0.1, 1]
-            for i, (R_pred, T_pred, weight) in enumerate(zip(rotation_preds, translation_preds,
-                                                             weights[-len(translation_preds):])):
-                if R_pred.shape[-1] == 9:
-                    R_pred = R_pred.reshape(-1, 3, 3)
+            res_rs, res_ts = [], []
+            # the samples of a step are independent: each keeps its own common point count (voxel_odom_net.py:646-651)
+            for smp in range(S):
+                fr = slice(smp * T, (smp + 1) * T)
+                pr = slice(smp * n_pairs, (smp + 1) * n_pairs)
+                points = [[p[:, cols][None]] for p in feats[fr]]
+                point_confs = [p[None] for p in preds_dict["middle_conf_preds"][fr]]
+                min_len = min(p[0].shape[1] for p in points)
+                points = [[p[0][:, :min_len]] for p in points]
+                point_confs = create_cycle_constraint_data([p[:, :min_len] for p in point_confs])
+                new_points = []
+                for h, _ in enumerate(points[0]):
+                    new_points.append(create_cycle_constraint_data([points[t][h] for t in range(len(points))], 1))
+                if len(new_points) < len(rotation_preds):
+                    new_points = new_points + [new_points[-1]] * (len(rotation_preds) - len(new_points))
                 else:
-                    R_pred = pose_utils.quaternion_to_rotation_matrix(roll(R_pred, shift=-1, dim=-1))
-                if step <= 1500:
-                    R_pred = torch.eye(3, device=device, dtype=dtype).expand(R_pred.shape[0], 3, 3).contiguous()
-                    T_pred = torch.zeros_like(T_pred)
-                p0, p1 = new_points[-(i + 1)][0], new_points[-(i + 1)][1]
-                transformed_p1_gt = p1[:, :, :3] @ R_pred.transpose(1, 2) + T_pred[:, None, :]
-                transformed_p1 = p0[:, :, :3]
-                transformed_normal1_gt = p1[:, :, 3:] @ R_pred.detach().transpose(1, 2)
-                transformed_normal1 = p0[:, :, 3:]
-                icp_iter = self.icp_iter if step > 1500 else 5
-                l, res_r, res_t = consistency_loss(
-                    transformed_p1, transformed_p1_gt, cov_pred=point_confs[0], cov_target=point_confs[1],
-                    R_pred=R_pred, t_pred=T_pred, normal_pred=transformed_normal1.detach(),
-                    normal_target=transformed_normal1_gt.detach(), mask=None, icp_iter=icp_iter)
-                C_loss = C_loss + (1 - warm_weight) * weight * l
+                    new_points = new_points[:len(rotation_preds)]
+                for i, (R_pred, T_pred, weight) in enumerate(zip(rotation_preds, translation_preds,
+                                                                 weights[-len(translation_preds):])):
+                    R_pred, T_pred = R_pred[pr], T_pred[pr]
+                    if R_pred.shape[-1] == 9:
+                        R_pred = R_pred.reshape(-1, 3, 3)
+                    else:
+                        R_pred = pose_utils.quaternion_to_rotation_matrix(roll(R_pred, shift=-1, dim=-1))
+                    if step <= 1500:
+                        R_pred = torch.eye(3, device=device, dtype=dtype).expand(R_pred.shape[0], 3, 3).contiguous()
+                        T_pred = torch.zeros_like(T_pred)
+                    p0, p1 = new_points[-(i + 1)][0], new_points[-(i + 1)][1]
+                    transformed_p1_gt = p1[:, :, :3] @ R_pred.transpose(1, 2) + T_pred[:, None, :]
+                    transformed_p1 = p0[:, :, :3]
+                    transformed_normal1_gt = p1[:, :, 3:] @ R_pred.detach().transpose(1, 2)
+                    transformed_normal1 = p0[:, :, 3:]
+                    icp_iter = self.icp_iter if step > 1500 else 5
+                    l, res_r, res_t = consistency_loss(
+                        transformed_p1, transformed_p1_gt, cov_pred=point_confs[0], cov_target=point_confs[1],
+                        R_pred=R_pred, t_pred=T_pred, normal_pred=transformed_normal1.detach(),
+                        normal_target=transformed_normal1_gt.detach(), mask=None, icp_iter=icp_iter)
+                    C_loss = C_loss + (1 - warm_weight) * weight * l / S
+                res_rs.append(res_r)
+                res_ts.append(res_t)
+            res_r, res_t = (res_rs[0], res_ts[0]) if S == 1 else (torch.cat(res_rs), torch.cat(res_ts))
 
         if (res_r is not None and len(pyramid_preds) > 0 and len(translation_preds) == 1
                 and pyramid_translation_loss is not None and pyramid_rotation_loss is not None):
@@ -453,7 +479,13 @@ class UnVoxelOdomNetICP3(nn.Module):
             return T_loss, R_loss, pyramid_T_losses, pyramid_R_losses, C_loss
 
         if res_r is not None and res_t is not None:
-            rotation_targets, translation_targets = self._pseudo_labels(res_r, res_t, R_pred, T_pred)
+            R_all, T_all = rotation_preds[-1], translation_preds[-1]
+            R_all = R_all.reshape(-1, 3, 3) if R_all.shape[-1] == 9 else \
+                pose_utils.quaternion_to_rotation_matrix(roll(R_all, shift=-1, dim=-1))
+            if step <= 1500:
+                R_all = torch.eye(3, device=device, dtype=dtype).expand(R_all.shape[0], 3, 3).contiguous()
+                T_all = torch.zeros_like(T_all)
+            rotation_targets, translation_targets = self._pseudo_labels(res_r, res_t, R_all, T_all)
 
         if len(pyramid_preds) > 0:
             tq_map_targets = self.gen_tq_maps(

@@ -36,9 +36,11 @@ pairs = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in 
 
 def step():
     red.zero_()
+    pts = []
     for a, b in pairs:
-        ret = net({"points": [a, b], "host_outputs": False})
-        (ret["loss"].sum() / len(pairs)).backward()
+        pts += [a, b]
+    ret = net({"points": pts, "n_samples": len(pairs), "host_outputs": False})
+    ret["loss"].sum().backward()
 
 
 for _ in range(4):

@@ -2,7 +2,12 @@
 against the same module tree evaluated by torch in FLOAT64 (`_trunk_torch`, the reference's layer sequence
 `rslo/models/odom_pred.py:152-260`): outputs, input gradients, every parameter gradient, BatchNorm running
 statistics; training mode with per-sample statistics groups, frozen-BN mode and eval mode.
-Tolerance: 2e-5 of the tensor's max magnitude (split-TF32 products are FP32-level; measured ~1e-6)."""
+Tolerances.  Forward outputs: 2e-5 of the tensor's max magnitude (split-TF32 products are FP32-level; measured
+1e-7 .. 6e-6).  Gradients: backpropagation through ~35 BatchNorm + ReLU layers with random weights amplifies
+rounding noise by ~1e4 (torch's own FP32/cuDNN evaluation of the same trunk is 1e-3 .. 7e-3 away from float64,
+measured on B200), so each gradient's relative L2 error is bounded by a multiple of the error that torch-FP32
+shows on the same tensor (the reference's arithmetic), with an absolute floor.  The formulas themselves are pinned
+tightly by the kernel-level tests below (1e-5 on well-conditioned inputs)."""
 import copy
 
 import numpy as np
@@ -42,6 +47,31 @@ def _inputs(S, seed, H=96, W=176, C=128):
 def _rel(a, b):
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _torch32_grads(head, state0, x1, x2, groups, seed):
+    """the reference's arithmetic: torch / cuDNN FP32, sample by sample"""
+    stash = {k: head.__dict__.pop(k) for k in ("_trunk_engine", "_graphed") if k in head.__dict__}
+    h32 = copy.deepcopy(head)
+    head.__dict__.update(stash)
+    h32.load_state_dict(state0)
+    h32.zero_grad()
+    outs, xs = [], []
+    n = x1.shape[0] // groups
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False, benchmark=False):
+        for s in range(groups):
+            a = x1[s * n:(s + 1) * n].detach().requires_grad_(True)
+            b = x2[s * n:(s + 1) * n].detach().requires_grad_(True)
+            xs.append((a, b))
+            tq, tl, rl, py, _ = h32._trunk_torch(a, b)
+            outs.append([tq, tl, rl] + py)
+        _loss([torch.cat(v) for v in zip(*outs)], seed).backward()
+    return h32, torch.cat([p[0].grad for p in xs]), torch.cat([p[1].grad for p in xs])
 
 
 def _ref_trunk(head, x1, x2, groups):
@@ -108,25 +138,27 @@ def test_trunk_matches_float64(head, mode, S):
         return
     _loss(outs, 1).backward()
     _loss(ref, 1).backward()
+    h32, g32x1, g32x2 = _torch32_grads(head, state0, x1, x2, S, 1)
     gx1 = torch.cat([p[0].grad for p in ref_x])
     gx2 = torch.cat([p[1].grad for p in ref_x])
-    assert _rel(a.grad, gx1) < 2e-5, _rel(a.grad, gx1)
-    assert _rel(b.grad, gx2) < 2e-5, _rel(b.grad, gx2)
-    p64 = dict(h64.named_parameters())
-    worst = ("", 0.0)
+    FACTOR, FLOOR = 8.0, 5e-5
+    assert _l2(a.grad, gx1) < max(FACTOR * _l2(g32x1, gx1), FLOOR), (_l2(a.grad, gx1), _l2(g32x1, gx1))
+    assert _l2(b.grad, gx2) < max(FACTOR * _l2(g32x2, gx2), FLOOR), (_l2(b.grad, gx2), _l2(g32x2, gx2))
+    p64, p32 = dict(h64.named_parameters()), dict(h32.named_parameters())
+    checked = 0
     for k, p in head.named_parameters():
         r = p64[k].grad
         if r is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert p.grad is not None, k
-        scale = float(r.abs().max())
-        if k.endswith(".bias") and scale < 1e-6 * max(1.0, float(p64[k[:-5] + ".weight"].grad.abs().max())):
-            continue                           # bias ahead of a batch-statistics BN: the true gradient is 0 (noise)
-        e = _rel(p.grad, r)
-        if e > worst[1]:
-            worst = (k, e)
-    assert worst[1] < 5e-5, worst
+        if k.endswith(".bias") and float(r.abs().max()) < 1e-9:
+            assert float(p.grad.abs().max()) < 1e-4, k      # bias ahead of a batch-statistics BN: true gradient 0
+            continue
+        e, e32 = _l2(p.grad, r), _l2(p32[k].grad, r)
+        assert e < max(FACTOR * e32, FLOOR), (k, e, e32)
+        checked += 1
+    assert checked > 120
     head.zero_grad()
 
 
@@ -169,3 +201,101 @@ def test_weight_update_through_data_is_seen(head):
         o1 = head._trunk_own(x1, x2, 1)[0].clone()
         w.data.div_(1.5)
     assert float((o1 - o0).abs().max()) > 1e-6
+
+
+# ---- kernel-level tests of csrc/head_ops.cu through the C ABI (well-conditioned inputs, tight tolerance) --------
+@pytest.mark.parametrize("B,H,W,C,ipg,relu,res,train", [(2, 12, 22, 256, 1, True, True, True), (3, 24, 20, 64, 3, True, False, True),
+                                                       (2, 16, 8, 32, 2, False, False, True), (2, 12, 22, 128, 1, True, True, False)])
+def test_bn_act_forward_backward_kernels(cuda, B, H, W, C, ipg, relu, res, train):
+    from rslo_b200 import kernels as K
+    g = torch.Generator().manual_seed(B * 100 + C)
+    y = (torch.randn(B, H, W, C, generator=g) * 2 + 0.3).cuda()
+    r = torch.randn(B, H, W, C, generator=g).cuda() if res else None
+    gamma = (0.5 + torch.rand(C, generator=g)).cuda()
+    beta = (0.3 * torch.randn(C, generator=g)).cuda()
+    rm = (0.1 * torch.randn(C, generator=g)).cuda()
+    rv = (0.5 + torch.rand(C, generator=g)).cuda()
+    dz = torch.randn(B, H, W, C, generator=g).cuda()
+    G = B // ipg
+    eps, mom = 1e-3, 0.01
+    # float64 reference, group by group (torch.nn.functional.batch_norm on NCHW)
+    yd = y.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rd = r.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True) if res else None
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    zs = []
+    for gi in range(G):
+        sl = slice(gi * ipg, (gi + 1) * ipg)
+        o = torch.nn.functional.batch_norm(yd[sl], rm_ref, rv_ref, gd, bd, training=train, momentum=mom, eps=eps)
+        if res:
+            o = o + rd[sl]
+        zs.append(torch.relu(o) if relu else o)
+    zd = torch.cat(zs)
+    zd.backward(dz.double().permute(0, 3, 1, 2))
+
+    stats = None
+    if train:
+        yg = y.double().view(G, ipg * H * W, C)
+        stats = torch.stack([yg.sum(1), (yg * yg).sum(1)], dim=-1).contiguous()
+    z = torch.empty_like(y)
+    zsplit = torch.empty((2,) + tuple(y.shape), device="cuda")
+    mr = torch.empty(G, C, 2, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    rm_k, rv_k = rm.clone(), rv.clone()
+    K.bn_act_forward(y, ipg, stats, gamma, beta, rm_k, rv_k, nbt, eps, mom, 1 if train else 0, r, relu, z, zsplit, mr)
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    assert rel(z, zd.permute(0, 2, 3, 1)) < 1e-5
+    assert torch.equal(zsplit[0] + zsplit[1], z) and float((zsplit[1].abs() > zsplit[0].abs() * 2 ** -10 + 1e-30).sum()) == 0
+    if train:
+        assert rel(rm_k, rm_ref) < 1e-6 and rel(rv_k, rv_ref) < 1e-6 and int(nbt) == G
+    sums = torch.zeros(G, C, 2, dtype=torch.float64, device="cuda")
+    gsplit = torch.empty((2,) + tuple(y.shape), device="cuda")
+    dres = torch.full_like(y, 7.0) if res else None
+    dgamma, dbeta, dbias = (torch.empty(C, device="cuda") for _ in range(3))
+    K.bn_act_backward(dz, z, y, ipg, mr, gamma, relu, train, sums, gsplit, dres, True, dgamma, dbeta, dbias)
+    assert rel(gsplit[0] + gsplit[1], yd.grad.permute(0, 2, 3, 1)) < 1e-5
+    assert rel(dgamma, gd.grad) < 1e-5 and rel(dbeta, bd.grad) < 1e-5
+    if res:
+        assert rel(dres - 7.0, rd.grad.permute(0, 2, 3, 1)) < 1e-5          # accumulate mode
+    if train:
+        assert float(dbias.abs().max()) == 0.0
+    else:
+        assert rel(dbias, yd.grad.sum(dim=(0, 2, 3))) < 1e-5
+
+
+def test_pack_unpack_upcat_kernels(cuda):
+    from rslo_b200 import kernels as K
+    g = torch.Generator().manual_seed(2)
+    B, C, H, W = 2, 64, 10, 12
+    x1 = torch.randn(B, C, H, W, generator=g).cuda()
+    x2 = torch.randn(B, C, H, W, generator=g).cuda()
+    x1[:, :, ::3, ::2] = 0
+    split = torch.empty(2, B, H, W, 2 * C, device="cuda")
+    mask = torch.empty(B, H, W, device="cuda")
+    K.head_pack_input(x1, x2, split, mask)
+    cat = torch.cat([x1, x2], 1).permute(0, 2, 3, 1)
+    assert torch.equal(split[0] + split[1], cat)
+    assert torch.equal(mask, (x1.sum(1) != 0).float())
+    dx = torch.randn(B, H, W, 2 * C, generator=g).cuda()
+    g1, g2 = torch.empty_like(x1), torch.empty_like(x2)
+    K.head_unpack_grad(dx, g1, g2)
+    assert torch.equal(g1, dx[..., :C].permute(0, 3, 1, 2)) and torch.equal(g2, dx[..., C:].permute(0, 3, 1, 2))
+    # upsample x2 + concat at a channel offset, and its adjoint
+    z = torch.randn(B, H, W, 32, generator=g).cuda()
+    ld, off = 96, 64
+    dst = torch.zeros(2, B, 2 * H, 2 * W, ld, device="cuda")
+    K.upcat_split(z, 2, ld, off, dst)
+    up = torch.nn.functional.interpolate(z.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal((dst[0] + dst[1])[..., off:off + 32], up) and float(dst[..., :off].abs().max()) == 0
+    dcat = torch.randn(B, 2 * H, 2 * W, ld, generator=g).cuda()
+    dz = torch.ones(B, H, W, 32, device="cuda")
+    K.upcat_backward(dcat, (B, H, W, 32), 2, ld, off, dz, True)
+    ref = dcat[..., off:off + 32].view(B, H, 2, W, 2, 32).double().sum(dim=(2, 4)) + 1
+    assert float((dz.double() - ref).abs().max()) < 1e-5
+    # narrow-head bias gradient
+    gg = torch.randn(B * H * W, 32, generator=g).cuda()
+    out = torch.zeros(7, device="cuda")
+    K.bias_grad(gg, B * H * W, 32, 7, out)
+    assert float((out.double() - gg[:, :7].double().sum(0)).abs().max()) < 1e-3

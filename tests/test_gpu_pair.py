@@ -163,3 +163,45 @@ def test_prepared_example_matches_direct_call(net):
     for k in ("translation_preds", "rotation_preds", "tq_map_g"):
         assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
 
+
+
+def test_two_samples_in_one_call_equal_two_calls(net):
+    """example["n_samples"] = 2 (one encoder pass over 4 frames, one head pass over 2 pairs with per-sample
+    BatchNorm statistics, one backward) == two single-sample calls with gradient accumulation of loss / 2."""
+    net, vg = net
+    onet.fill_weights(net, 11)
+    net.global_step.fill_(2000)
+    net._step_host = None
+    net.train()
+    fa = mg.make_frames(3, 16, 600, 2)
+    fb = mg.make_frames(4, 16, 600, 2)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    net.zero_grad()
+    losses, poses = [], []
+    for fr in (fa, fb):
+        ret = net({"points": [torch.from_numpy(f).cuda() for f in fr], "host_outputs": False})
+        (ret["loss"].sum() / 2).backward()
+        losses.append(float(ret["loss"].detach().sum()))
+        poses.append(torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1))
+        # gradients handed out by a CUDA-graph replay alias the graph's static buffers (torch steals them into
+        # p.grad when it was None); take ownership before the same graph is replayed again (INTEGRATION.md)
+        for p in net.parameters():
+            if p.grad is not None:
+                p.grad = p.grad.clone()
+    g_ref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    sd_seq = {k: v.clone() for k, v in net.state_dict().items()}
+    net.load_state_dict(sd0)
+    net.zero_grad()
+    ret = net({"points": [torch.from_numpy(f).cuda() for f in fa + fb], "n_samples": 2, "host_outputs": False})
+    ret["loss"].sum().backward()
+    np.testing.assert_allclose(float(ret["loss"].sum()), 0.5 * (losses[0] + losses[1]), rtol=2e-5)
+    pose = torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1)
+    assert _rel(pose.cpu().numpy(), torch.cat(poses).cpu().numpy()) < 1e-5
+    for k, p in net.named_parameters():
+        if k in g_ref and float(g_ref[k].abs().max()) > 0:
+            assert p.grad is not None, k
+            assert _rel(p.grad.cpu().numpy(), g_ref[k].cpu().numpy()) < 2e-3, k
+    # BatchNorm running statistics advanced sample after sample, exactly as in the two calls
+    for k, v in net.state_dict().items():
+        if "running_" in k or "num_batches_tracked" in k:
+            assert _rel(v.double().cpu().numpy(), sd_seq[k].double().cpu().numpy()) < 1e-5, k
