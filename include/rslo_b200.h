@@ -246,6 +246,49 @@ int rslo_upcat_backward(const float* dcat, int B, int H, int W, int C, int up, i
 /* out[c] += sum_rows g[row][c] for c < C <= 32, g [N][ld] (bias gradient of the 7- / 1-channel output convs) */
 int rslo_bias_grad(const float* g, int N, int ld, int C, float* out, rslo_stream_t stream);
 
+/* ---- a9 / a13: the two tails of the head (csrc/pose_tail.cu), one launch forward + one backward each --------
+ * Geometry of the (t,q) map: cell (i,j) has its anchor at x = (j - ox) vsx, y = (-i + oy) vsy, z = (0 - oz) vsz
+ * (rslo/data/dataset.py:145-146,169-171). */
+typedef struct {
+    int H, W;
+    float ox, oy, oz, vsx, vsy, vsz;
+} rslo_tq_geom_t;
+/* Head tail (rslo/models/odom_pred.py:226-313, rslo/layers/confidence.py:23-34, rslo/data/dataset.py:121-208):
+ * inputs NHWC with 32-channel rows as written by the trunk's output convolutions: tq32 [B][H][W][32] (7 used),
+ * t_logit32 / r_logit32 (1 used), py0_32 [B][H/4][W/4][32], py1_32 [B][H/2][W/2][32] (7 used), mask [B][H][W].
+ * outputs (NCHW as in the reference): pose_t [B,3], pose_q [B,4] (w,x,y,z, unit), tq_map_g [B,7,H,W] (masked),
+ * t_conf / r_conf [B,1,H,W], pyramid_motion levels 2 (full), 1 (H/2), 0 (H/4): pred [B,7,h,w], mask [B,2,h,w];
+ * occ1 [B,H/2,W/2], occ0 [B,H/4,W/4] (max-pooled occupancy) and save [B][16] are kept for the backward. */
+int rslo_head_tail_forward(const float* tq32, const float* t_logit32, const float* r_logit32, const float* mask,
+                           const float* py0_32, const float* py1_32, int B, rslo_tq_geom_t geom, float* pose_t,
+                           float* pose_q, float* tq_map_g, float* t_conf, float* r_conf, float* pm2_pred,
+                           float* pm2_mask, float* pm1_pred, float* pm1_mask, float* pm0_pred, float* pm0_mask,
+                           float* occ1, float* occ0, float* save, rslo_stream_t stream);
+/* gradient inputs may be NULL (no gradient); outputs are full 32-channel rows (zeros in the unused channels) */
+int rslo_head_tail_backward(const float* tq32, const float* mask, const float* t_conf, const float* r_conf,
+                            const float* occ1, const float* occ0, const float* save, int B, rslo_tq_geom_t geom,
+                            const float* g_pose_t, const float* g_pose_q, const float* g_tq_map_g,
+                            const float* g_t_conf, const float* g_r_conf, const float* g_pm2_pred,
+                            const float* g_pm1_pred, const float* g_pm0_pred, float* d_tq32, float* d_t_logit32,
+                            float* d_r_logit32, float* d_py1_32, float* d_py0_32, rslo_stream_t stream);
+/* Loss tail (rslo/models/voxel_odom_net.py:727-795, rslo/data/dataset.py:52-116, rslo/core/losses.py:155-197 with
+ * focal_gamma 0): pseudo labels R* = res_r R(q_pred) (identity while identity_pose), t* = res_r T + res_t ->
+ * target map tq_target [B,7,H,W]; losses8 = {T, R, pyramid T x3 (levels 0,1,2), pyramid R x3}, each
+ * w (sum_b e^-alpha L_b / (B + 1e-12) + alpha).  alpha_*: device scalars (may alias).  save: [B][24] floats;
+ * counter: one zeroed device int (left zeroed). */
+int rslo_loss_tail_forward(const float* T_pred, const float* q_pred, const float* pm0_pred, const float* pm0_mask,
+                           const float* pm1_pred, const float* pm1_mask, const float* pm2_pred, const float* pm2_mask,
+                           const float* res_r, const float* res_t, int identity_pose, int B, rslo_tq_geom_t geom,
+                           const float* alpha_t, const float* alpha_r, const float* alpha_pt, const float* alpha_pr,
+                           float w_t, float w_r, float w_pt, float w_pr, float* tq_target, float* save, float* losses8,
+                           int* counter, rslo_stream_t stream);
+int rslo_loss_tail_backward(const float* T_pred, const float* q_pred, const float* pm0_pred, const float* pm0_mask,
+                            const float* pm1_pred, const float* pm1_mask, const float* pm2_pred, const float* pm2_mask,
+                            int B, rslo_tq_geom_t geom, const float* alpha_t, const float* alpha_r,
+                            const float* alpha_pt, const float* alpha_pr, float w_t, float w_r, float w_pt, float w_pr,
+                            const float* save, const float* g_losses8, float* dT, float* dq, float* d_pm0, float* d_pm1,
+                            float* d_pm2, float* dalpha4, rslo_stream_t stream);
+
 /* ---- a7: SparseConvTensor.dense() + view (middle.py:240-243) ------------------------------------
  * feat [n,C] at sites of a (D,H,W) level -> dense [C*D, H, W] f32 (zero where no site). */
 int rslo_dense_from_sites(const float* feat, int C, const uint32_t* cells, const int32_t* perm,

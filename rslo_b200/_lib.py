@@ -17,6 +17,12 @@ lib = C.CDLL(LIB_PATH)
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
+
+class TqGeom(C.Structure):               # rslo_tq_geom_t
+    _fields_ = [("H", C.c_int), ("W", C.c_int), ("ox", C.c_float), ("oy", C.c_float), ("oz", C.c_float),
+                ("vsx", C.c_float), ("vsy", C.c_float), ("vsz", C.c_float)]
+
+
 # name -> (restype, argtypes); mirrors include/rslo_b200.h one to one
 SIGNATURES = {
     "rslo_abi_version": (_i, []),
@@ -65,6 +71,10 @@ SIGNATURES = {
     "rslo_upcat_split": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rslo_upcat_backward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "rslo_bias_grad": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "rslo_head_tail_forward": (_i, [_vp] * 6 + [_i, TqGeom] + [_vp] * 14 + [_vp]),
+    "rslo_head_tail_backward": (_i, [_vp] * 7 + [_i, TqGeom] + [_vp] * 13 + [_vp]),
+    "rslo_loss_tail_forward": (_i, [_vp] * 10 + [_i, _i, TqGeom] + [_vp] * 4 + [_f] * 4 + [_vp] * 4 + [_vp]),
+    "rslo_loss_tail_backward": (_i, [_vp] * 8 + [_i, TqGeom] + [_vp] * 4 + [_f] * 4 + [_vp] * 8 + [_vp]),
     "rslo_dense_from_sites": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rslo_kabsch_workspace_bytes": (_sz, []),
     "rslo_kabsch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

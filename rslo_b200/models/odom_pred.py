@@ -22,6 +22,7 @@ from ..layers.common import ParameterLayer
 from ..layers.confidence import ConfidenceModule
 from ..layers.conv2d_tc import Conv2dTC
 from ..layers.head_tc import HeadTrunkEngine, head_trunk
+from ..layers.pose_tail import head_geometry, head_tail
 from ..layers.MaskConv import MaskConv
 from ..layers.SparseConv import SPC_BN2d, SPC_ReLU, SPC_SyncBN2d
 from ..torchplus import Empty, change_default_args
@@ -35,6 +36,9 @@ HEAD_ALLOW_TF32 = False
 # The trunk runs on the repo's own tcgen05 convolutions + fused BN/ReLU kernels (layers/head_tc.py).
 # RSLO_HEAD_TC=0 switches to torch/cuDNN FP32 for A/B comparison only.
 USE_OWN_TRUNK = os.environ.get("RSLO_HEAD_TC", "1") != "0"
+# The tail after the last convolution (confidences, local->global, vote, pyramid masks) is one fused kernel
+# (layers/pose_tail.py); RSLO_HEAD_TAIL=0 runs the same steps as torch ops (A/B comparison).
+USE_OWN_TAIL = os.environ.get("RSLO_HEAD_TAIL", "1") != "0"
 # cuDNN autotuning of the head's FP32 convolutions (shapes are static; tuned once before graph capture).
 HEAD_CUDNN_BENCHMARK = os.environ.get("RSLO_CUDNN_BENCHMARK", "1") != "0"
 
@@ -326,11 +330,26 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
             xs = self.create_cycle_constraint_data(xs)
         x1, x2 = xs
         if USE_OWN_TRUNK and x1.is_cuda:
+            if (USE_OWN_TAIL and self.pred_pyramid_motion and len(self.deblocks) == 3 and self.conf_type == "softmax"
+                    and self.odom_format == "rx+t"):
+                # trunk + fused tail kernel (csrc/pose_tail.cu): no torch op between the last convolution and the pose
+                outs = head_trunk(self._engine(), x1, x2, imgs_per_group or x1.shape[0])
+                geom = self.__dict__.get("_tail_geom")
+                if geom is None or (geom.H, geom.W) != tuple(x1.shape[2:]):
+                    geom = self.__dict__["_tail_geom"] = head_geometry(x1.shape[2], x1.shape[3], self.point_cloud_range)
+                t, q, tq_map_g, t_conf, r_conf, pyramid = head_tail(outs[0], outs[1], outs[2], outs[3], outs[4], outs[5], geom)
+                return {"translation_preds": [t], "rotation_preds": [q], "tq_map_g": tq_map_g, "pyramid_motion": pyramid,
+                        "transformed_inputs": None, "t_conf": t_conf, "r_conf": r_conf}
             tq_map, t_logit, r_logit, py_raw, input_mask = self._trunk_own(x1, x2, imgs_per_group)
         else:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=HEAD_ALLOW_TF32, benchmark=HEAD_CUDNN_BENCHMARK):
                 tq_map, t_logit, r_logit, py_raw, input_mask = self._trunk_torch(x1, x2)
 
+        return self._tail_torch(tq_map, t_logit, r_logit, py_raw, input_mask)
+
+    def _tail_torch(self, tq_map, t_logit, r_logit, py_raw, input_mask):
+        """`odom_pred.py:210-313` after the convolutions as torch ops (A/B switch RSLO_HEAD_TAIL=0, CPU, and the
+        float64 yardstick of tests/test_gpu_tail.py); the default GPU path is layers/pose_tail.py."""
         py_masks = []
         if self.pred_pyramid_motion:
             p_mask = input_mask

@@ -21,6 +21,7 @@ from torch.nn import functional as F
 
 from .. import kernels as K
 from ..data.dataset import generate_pointwise_local_transformation_tch
+from ..layers.pose_tail import loss_geometry, loss_tail
 from ..torchplus import roll
 from ..utils import pose_utils
 from . import middle, odom_pred, voxel_encoder
@@ -553,38 +554,25 @@ class UnVoxelOdomNetICP3(nn.Module):
         return (T_loss, R_loss, *pyT, *pyR, tq_map)
 
     def _loss_tail(self, T_pred, q_pred, pyramid_preds, res_r, res_t, identity_pose):
+        """pseudo labels -> target maps -> pose + pyramid losses: one fused kernel forward, one backward
+        (layers/pose_tail.py over csrc/pose_tail.cu) when the configuration is the shipped one; otherwise the same
+        steps as torch ops."""
         flat = []
         for pred, mask in pyramid_preds:
             flat += [pred, mask]
-        use_graph = odom_pred.UNRResNetOdomPredEncDecSVDTempMask.use_cuda_graph and T_pred.is_cuda
-        if not use_graph:
+        mods = (self._translation_loss, self._rotation_loss, self._pyramid_translation_loss, self._pyramid_rotation_loss)
+        fused = (odom_pred.USE_OWN_TAIL and T_pred.is_cuda and len(pyramid_preds) == 3
+                 and all(getattr(m, "focal_gamma", 1) == 0 for m in mods)
+                 and not (self.odom_predictor._cubic_pred_height > 0)
+                 and pyramid_preds[0][0].shape[2] * 4 == pyramid_preds[2][0].shape[2]
+                 and pyramid_preds[1][0].shape[2] * 2 == pyramid_preds[2][0].shape[2])
+        if not fused:
             return self._loss_tail_eager(T_pred, q_pred, flat, res_r, res_t, identity_pose)
-        args = (T_pred, q_pred, *flat, res_r, res_t)
-        key = (identity_pose, self._translation_loss._loss_weight, self._rotation_loss._loss_weight,
-               tuple((tuple(a.shape), a.requires_grad) for a in args), T_pred.device.index,
-               torch.cuda.current_stream().cuda_stream)
-        cache = self.__dict__.setdefault("_graphed_tail", {})
-        g = cache.get(key)
-        if g is None:
-            mod = _LossTail(self, identity_pose)
-            sample = tuple(torch.rand_like(a).add_(0.5).requires_grad_(a.requires_grad) for a in args)
-            with torch.enable_grad():
-                g = torch.cuda.make_graphed_callables(mod, sample, allow_unused_input=True)
-            cache[key] = g
-        outs = g(*[a.contiguous() for a in args])
-        return tuple(o.clone() for o in outs)               # static graph buffers -> caller-owned tensors
-
-
-class _LossTail(nn.Module):
-    """Tensor-in / tensor-out view of the loss tail for CUDA-graph capture; shares the net's loss
-    modules (their learnable alphas are this module's parameters).  Never registered as a child of the
-    net, so the state_dict is unchanged."""
-
-    def __init__(self, net, identity_pose):
-        super().__init__()
-        self.__dict__["_net"] = net                          # plain reference, not a submodule
-        self.t_loss, self.r_loss = net._translation_loss, net._rotation_loss
-        self.identity_pose = identity_pose
-
-    def forward(self, T_pred, q_pred, *rest):
-        return self._net._loss_tail_eager(T_pred, q_pred, list(rest[:-2]), rest[-2], rest[-1], self.identity_pose)
+        H, W = pyramid_preds[2][0].shape[2:]
+        geom = self.__dict__.get("_loss_geom")
+        if geom is None or (geom.H, geom.W) != (H, W):
+            geom = self.__dict__["_loss_geom"] = loss_geometry(H, W, self.odom_predictor.point_cloud_range)
+        T_loss, R_loss, pyT, pyR, tq_map = loss_tail(T_pred, q_pred, pyramid_preds, res_r, res_t,
+                                                     [m.alpha for m in mods], [m._loss_weight for m in mods],
+                                                     identity_pose, geom)
+        return (T_loss, R_loss, *pyT, *pyR, tq_map)
