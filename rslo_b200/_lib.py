@@ -119,8 +119,16 @@ def ptr(t):
 
 
 def stream():
+    """current CUDA stream of the current device as a raw handle (torch.cuda.current_stream() costs ~15 us of host
+    time per call; this is on the path of every kernel launch)"""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+def raw_stream():
+    import torch
+    dev = torch._C._cuda_getDevice()
+    return dev, torch._C._cuda_getCurrentRawStream(dev)
 
 
 _WS = {}
@@ -130,8 +138,8 @@ def workspace(nbytes, slot="default"):
     """Growable per-(device, stream, slot) scratch buffer: reuse is ordered by the stream it belongs to, so
     work on different streams (preparation stream, concurrent examples) never shares scratch memory."""
     import torch
-    dev = torch.cuda.current_device()
-    key = (dev, torch.cuda.current_stream().cuda_stream, slot)
+    dev, st = raw_stream()
+    key = (dev, st, slot)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=f"cuda:{dev}")

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import check, lib, ptr, stream, workspace
+from ._lib import check, lib, ptr, raw_stream, stream, workspace
 
 LAUNCHES = {"calls": 0}
 PROFILE = None      # set to a list to record (name, start_event, end_event, algorithmic_bytes, flops) per call
@@ -487,8 +487,8 @@ _CONV_WS = {}
 def _conv_ws():
     """Per-(device, stream) split-K workspace of the dense convolutions; zeroed once (the kernels keep the
     tile counters zeroed between launches)."""
-    dev = torch.cuda.current_device()
-    key = (dev, torch.cuda.current_stream().cuda_stream)
+    key = raw_stream()
+    dev = key[0]
     ws = _CONV_WS.get(key)
     if ws is None:
         ws = torch.zeros(lib.rslo_conv2d_tc_workspace_bytes(0, 0, 0, 0), dtype=torch.uint8, device=f"cuda:{dev}")

@@ -249,22 +249,31 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
     def _apply(self, fn, *a, **k):
         # parameters may move (net.to(device)): captured graphs and prepared weight images point at the old storage
         self.__dict__.pop("_graphed", None)
+        self.__dict__.pop("_mode_sig", None)
         e = self.__dict__.get("_trunk_engine")
         if e is not None:
             e.clear()
         return super()._apply(fn, *a, **k)
 
+    def train(self, mode=True):
+        self.__dict__.pop("_mode_sig", None)
+        return super().train(mode)
+
     def _mode_signature(self):
         """what a captured graph bakes in besides shapes: per-layer BN mode (freeze_bn flips single layers to eval)
-        and which parameters receive gradients (freeze_bn_affine)"""
-        bn = tuple(m.training for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm))
-        rg = tuple(p.requires_grad for p in self.parameters())
-        return hash((bn, rg))
+        and which parameters receive gradients (freeze_bn_affine).  Cached; `train()` / `eval()` on the head or any
+        module above it (which is how the reference flips these, `voxel_odom_net.py:206-224`) and `_apply` reset it."""
+        sig = self.__dict__.get("_mode_sig")
+        if sig is None:
+            bn = tuple(m.training for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm))
+            rg = tuple(p.requires_grad for p in self.parameters())
+            sig = self.__dict__["_mode_sig"] = hash((bn, rg))
+        return sig
 
     def _forward_graphed(self, xs, ipg):
         # one captured graph per stream: replays on different streams must not share static buffers
         key = (len(xs), self.training, self._mode_signature(), tuple(x.requires_grad for x in xs), tuple(xs[0].shape),
-               xs[0].device.index, torch.cuda.current_stream().cuda_stream, torch.is_grad_enabled())
+               xs[0].device.index, torch._C._cuda_getCurrentRawStream(xs[0].device.index), torch.is_grad_enabled())
         cache = self.__dict__.setdefault("_graphed", {})
         g = cache.get(key)
         if g is None:
