@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py — frame-pairs/s of RSLO's per-frame-pair hot path on B200 (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|eval|stress] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|eval|warm|stress] [--impl reference]
 
 A step = one pass of the hot path over one batch of synthetic KITTI-shaped scans:
-  train (default; BASELINE.json configs[2]/[3]): 2 frame pairs per GPU, 120k-pt scans, 0.1 m voxels,
-        voxelise -> sparse encoder -> head -> loss, forward + backward (+ one flat gradient
-        all-reduce over NCCL when N > 1), global step > 1500 (icp_iter 2);
-  eval  (configs[1]): 1 pair per GPU, forward only.
-`value`   : pairs/s with the raw scans already resident in HBM.
-`e2e`     : the same through net(example) with HOST (pinned) scans: H2D of the points and D2H of the
+  train (default; BASELINE.json configs[2]/[3]): 2 frame pairs per GPU through ONE net(example) call
+        (example["n_samples"] = 2), 120k-pt scans, 0.1 m voxels, voxelise -> sparse encoder -> head -> loss,
+        forward + backward (+ one flat gradient all-reduce over NCCL when N > 1), global step > 1500 (icp_iter 2);
+  eval  (configs[1]): 1 pair per GPU, forward only;
+  warm  : train at global step <= 1500 (identity pose, icp_iter 5: `voxel_odom_net.py:677-695`);
+  stress (configs[4]): 300k-ray scans, 0.05 x 0.05 x 0.1 m voxels (grid 2816 x 1536 x 80), fwd+bwd.
+`value`   : pairs/s with the raw scans already resident in HBM (total time of exactly K steps).
+`e2e`     : the same through net.prepare / net(example) with HOST (pinned) scans: H2D of the points and D2H of the
             loss / pose inside the timed region.
-`roofline`: the dominant kernel (sparse-conv gather-GEMM) — algorithmic bytes / CUDA-event time,
-            measured on a profiled replica of the timed steps (events bracket every C-ABI call).
-`cpu_baseline`: the CPU oracle port (oracle/net.py) on this box's host cores, one pair.
---impl reference: times that CPU path alone (rank 0 only), same metric/config keys.
+`roofline`: the kernel with the largest summed time in a step (profiled replica with CUDA events around every
+            C-ABI call, head un-graphed for that replica) against the roofline that bounds it; `roofline_hbm`:
+            the largest HBM-bound own kernel.
+`cpu_baseline` / --impl reference: the CPU oracle port (oracle/net.py) on this box's host cores.
+`extra`   : (N = 1 only) the other BASELINE configs as pairs/s: eval, warm-up mode, dense-scan stress with a sweep of
+            the voxel cap, and the exact-NN kernel next to the reference's own CUDA kernel (oracle/_ref/cd_ref.so).
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -30,37 +35,52 @@ sys.path.insert(0, ROOT)
 METRIC = "frame-pairs/sec (fwd+bwd) on KITTI-shaped synthetic scans"
 WEIGHT_SEED = 11
 STEP_AFTER_WARMUP = 2000          # global step > 1500: predicted pose, icp_iter = 2 (voxel_odom_net.py:692-695)
+STEP_WARM_MODE = 100              # global step <= 1500: identity pose, icp_iter = 5
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="train", choices=["train", "eval", "stress"])
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="train", choices=["train", "eval", "warm", "stress"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=None)
+    ap.add_argument("--max-voxels", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=420.0)
     return ap.parse_args()
 
 
-def workload_config(args):
-    if args.workload == "eval":
-        ppg = args.pairs_per_gpu or 1
+def workload_config(workload, pairs_per_gpu=None, max_voxels=None):
+    if workload == "eval":
         return {"workload": "C2 eval fwd: 120k-pt pair (64 beams x 1875 az), voxel 0.1x0.1x0.2 m, <=40000 voxels/frame, "
-                            "kitti_eval_ours model", "mode": "eval", "pairs_per_gpu": ppg, "beams": 64, "n_az": 1875}
-    if args.workload == "stress":
-        ppg = args.pairs_per_gpu or 1
-        return {"workload": "C5 dense-scan stress: 128 beams x 2344 az (300k rays), voxel 0.05x0.05x0.2 m "
-                            "(grid 2816x1536x40, BEV 192x352), <=250000 voxels/frame, fwd+bwd",
-                "mode": "train", "pairs_per_gpu": ppg, "beams": 128, "n_az": 2344,
+                            "kitti_eval_ours model", "mode": "eval", "pairs_per_gpu": pairs_per_gpu or 1, "beams": 64,
+                "n_az": 1875, "global_step": STEP_AFTER_WARMUP}
+    if workload == "stress":
+        return {"workload": "C5 dense-scan stress: 128 beams x 2344 az (300k rays), voxel 0.05x0.05x0.1 m "
+                            f"(grid 2816x1536x80, BEV 192x352x256ch), <={max_voxels or 250000} voxels/frame, fwd+bwd",
+                "mode": "train", "pairs_per_gpu": pairs_per_gpu or 1, "beams": 128, "n_az": 2344,
+                "global_step": STEP_AFTER_WARMUP, "max_voxels": max_voxels or 250000,
                 "config_path": os.path.join(ROOT, "rslo_b200", "config", "stress_005.prototxt")}
-    ppg = args.pairs_per_gpu or 2
+    if workload == "warm":
+        return {"workload": "C3 warm-up mode: train fwd+bwd at global step <= 1500 (identity pose, icp_iter 5), 2 pairs per "
+                            "GPU, 120k-pt scans, voxel 0.1x0.1x0.2 m", "mode": "train", "pairs_per_gpu": pairs_per_gpu or 2,
+                "beams": 64, "n_az": 1875, "global_step": STEP_WARM_MODE}
     return {"workload": "C3/C4 train fwd+bwd: 2 pairs per GPU, 120k-pt scans (64 beams x 1875 az), voxel 0.1x0.1x0.2 m, "
                         "<=40000 voxels/frame, kitti_train_ours model section, Chamfer+covariance loss, step>1500",
-            "mode": "train", "pairs_per_gpu": ppg, "beams": 64, "n_az": 1875}
+            "mode": "train", "pairs_per_gpu": pairs_per_gpu or 2, "beams": 64, "n_az": 1875,
+            "global_step": STEP_AFTER_WARMUP}
+
+
+def public_config(cfg, world=1, extra=None):
+    out = {"workload": cfg["workload"], "mode": cfg["mode"], "pairs_per_gpu": cfg["pairs_per_gpu"],
+           "global_pairs_per_step": cfg["pairs_per_gpu"] * world, "parallelism": f"dp{world}",
+           "global_step": cfg["global_step"]}
+    out.update(extra or {})
+    return out
 
 
 def make_pairs(n, beams, n_az, first_seed):
@@ -73,47 +93,83 @@ def make_pairs(n, beams, n_az, first_seed):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm (oracle port): cpu_baseline and --impl reference
+# CPU arm (oracle port): cpu_baseline and --impl reference.  Nothing here imports the product's kernels:
+# the weights come from the committed shape table + the per-key deterministic fill.
 # ------------------------------------------------------------------------------------------------
+def reference_state_dict(seed):
+    import torch
+    spec = importlib.util.spec_from_file_location("_rslo_weights", os.path.join(ROOT, "rslo_b200", "utils", "weights.py"))
+    wmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(wmod)                       # plain torch/numpy module; does not load librslo_b200.so
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_shapes.json")))
+    sd = {}
+    for k, shp in shapes.items():
+        if k == "global_step" or k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros(shp, dtype=torch.long)
+        else:
+            sd[k] = torch.zeros(shp, dtype=torch.float32)
+    # values the deterministic fill leaves alone: the shipped config's initial values
+    sd["_rotation_loss.alpha"].fill_(-2.5)
+    sd["_pyramid_rotation_loss.alpha"].fill_(-2.5)
+    for k in sd:
+        if "dynamic_sigma" in k:
+            sd[k].fill_(0.1)
+    if "_consistency_loss.svd.reflect" in sd:
+        sd["_consistency_loss.svd.reflect"].copy_(torch.diag(torch.tensor([1.0, 1.0, -1.0])))
+    wmod.deterministic_fill(sd, seed)
+    return sd
+
+
 def cpu_run(cfg, steps, warmup, budget_s):
-    """Times the CPU restatement of the reference path (oracle/net.py; the reference's own Python
-    needs its un-vendored spconv/kornia/apex deps and cannot run on this box) on all host cores.
-    Each step = ONE pair of the workload (bounded sample)."""
+    """Times the CPU restatement of the reference path (oracle/net.py; the reference's own Python needs its
+    un-vendored spconv/kornia/apex deps and cannot run on this box) on all host cores.  A step = the same batch as the
+    B200 arm's step (pairs_per_gpu pairs, processed one after the other as the reference would)."""
     import torch
     from oracle import net as onet
-    import rslo_b200
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    net, _ = rslo_b200.build_network(testing=False, seed=7)
-    onet.fill_weights(net, WEIGHT_SEED)
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = reference_state_dict(WEIGHT_SEED)
     train = cfg["mode"] == "train"
-    keys = [k for k, p in net.named_parameters() if p.requires_grad] if train else ()
-    pairs = make_pairs(2, cfg["beams"], cfg["n_az"], 100)
+    keys = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var", "reflect"))
+            and k != "_consistency_loss.alpha"] if train else ()
+    ppg = cfg["pairs_per_gpu"]
+    pairs = make_pairs(max(2, ppg), cfg["beams"], cfg["n_az"], 100)
+
+    def one_step(i):
+        for j in range(ppg):
+            onet.pair_forward(sd, list(pairs[(i * ppg + j) % len(pairs)]), training=train, step=cfg["global_step"],
+                              grads_for=keys)
+
     t_all0 = time.time()
-    for i in range(min(warmup, 1)):
-        onet.pair_forward(sd, list(pairs[i % 2]), training=train, step=STEP_AFTER_WARMUP, grads_for=keys)
+    w_done = 0
+    for i in range(warmup):
+        one_step(i)
+        w_done += 1
+        if time.time() - t_all0 > budget_s / 3:
+            break
     done, t0 = 0, time.time()
     while done < steps:
-        onet.pair_forward(sd, list(pairs[done % 2]), training=train, step=STEP_AFTER_WARMUP, grads_for=keys)
+        one_step(done)
         done += 1
         if time.time() - t_all0 > budget_s:
             break
     dt = time.time() - t0
-    return {"value": done / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": f"{done} step(s) x 1 pair ({'fwd+bwd' if train else 'fwd'}) of the same workload, "
-                      f"torch CPU {cores} threads + C oracle (single-thread voxeliser/NN)"}, done, dt
+    return {"value": done * ppg / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{done} step(s) x {ppg} pair(s) ({'fwd+bwd' if train else 'fwd'}) of the same workload after "
+                      f"{w_done} warm-up step(s), torch CPU {cores} threads + C oracle (single-thread voxeliser/NN)"}, done, w_done, dt
 
 
 def reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, done, dt = cpu_run(cfg, args.steps, args.warmup, args.cpu_budget_s)
+    # bounded sample: the same step (same pairs per step, same mode) as the B200 arm, as many as fit the budget
+    cb, done, w_done, dt = cpu_run(cfg, args.steps, args.warmup, args.cpu_budget_s)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus,
-            "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / max(done, 1),
+            "steps": done, "warmup": w_done, "ms_per_step": 1e3 * dt / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {k: v for k, v in cfg.items() if k in ("workload", "mode", "pairs_per_gpu")},
+            "config": public_config(cfg, 1, {"note": "CPU arm: rank 0 only, one replica's batch per step; steps/warm-up "
+                                                     f"bounded by --cpu-budget-s {args.cpu_budget_s:.0f}"}),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -189,84 +245,82 @@ def measured_traffic(kernel):
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d = {}
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            if "hbm_gbs" in d:
-                return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
-            pass
-    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+            d = {}
+    hbm = (float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in d else \
+        (6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)")
+    if "bf16_tflops_sustained" in d:
+        tf32 = (float(d["bf16_tflops_sustained"]) / 2, "half of MEASURED_PEAKS.json bf16_tflops_sustained (kind::tf32 runs "
+                                                        "at half the bf16 rate; kernel timed inside a long step)")
+    else:
+        tf32 = (2250.0 / 2, "fallback: half of the nominal 2.25 PFLOP/s dense bf16")
+    return hbm, tf32
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def main():
-    args = parse_args()
-    cfg = workload_config(args)
-    if args.impl == "reference":
-        return reference_arm(args, cfg)
+class Runner:
+    """One workload on this rank: network, a pool of synthetic pairs (device-resident and pinned-host copies), the
+    step function through the public API (net.prepare on a side stream one step ahead, net(example), backward,
+    flat gradient all-reduce) and the timed loop."""
+    PREFETCH_DEPTH = 1
 
-    import torch
-    import torch.distributed as dist
-    import rslo_b200
-    from rslo_b200.utils.weights import deterministic_fill
-    from rslo_b200 import kernels as K
-    from rslo_b200.utils.distributed import FlatGradAllReducer, init_from_env
+    def __init__(self, cfg, dev, rank, world):
+        import torch
+        import rslo_b200
+        from rslo_b200.utils.distributed import FlatGradAllReducer
+        from rslo_b200.utils.weights import deterministic_fill
+        self.torch, self.cfg, self.dev, self.world = torch, cfg, dev, world
+        self.train = cfg["mode"] == "train"
+        self.ppg = cfg["pairs_per_gpu"]
+        net, vg = rslo_b200.build_network(cfg.get("config_path"), testing=False, seed=7)
+        if cfg.get("max_voxels"):
+            vg.max_voxels_per_call = int(cfg["max_voxels"])
+        deterministic_fill(net, WEIGHT_SEED)
+        net = net.to(dev)
+        net.global_step.fill_(cfg["global_step"])
+        net._step_host = None
+        net.train(self.train)
+        self.net, self.vg = net, vg
+        self.reducer = FlatGradAllReducer(net) if self.train else None
+        self.pool_n = max(2 * self.ppg, 4)
+        pairs = make_pairs(self.pool_n, cfg["beams"], cfg["n_az"], first_seed=1000 * rank)
+        self.host = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
+        self.resident = [(a.to(dev), b.to(dev)) for a, b in self.host]
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.image_caches = [m._images for m in net.modules() if hasattr(m, "_images")]
+        self.prefetch = {}
 
-    rank, local, world = init_from_env()
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    train = cfg["mode"] == "train"
-    ppg = cfg["pairs_per_gpu"]
-
-    net, vg = rslo_b200.build_network(cfg.get("config_path"), testing=False, seed=7)
-    deterministic_fill(net, WEIGHT_SEED)
-    net = net.to(dev)
-    net.global_step.fill_(STEP_AFTER_WARMUP)
-    net._step_host = None
-    net.train(train)
-    reducer = FlatGradAllReducer(net) if train else None
-
-    # inputs: a pool of distinct pairs per rank (rotated so no step re-reads the previous step's scans)
-    pool_n = max(2 * ppg, 4)
-    pairs = make_pairs(pool_n, cfg["beams"], cfg["n_az"], first_seed=1000 * rank)
-    host = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
-    resident = [(a.to(dev), b.to(dev)) for a, b in host]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-
-    h2d_bytes = [0]
-    d2h_bytes = [0]
-
-    image_caches = [m._images for m in net.modules() if hasattr(m, "_images")]
-    PREFETCH_DEPTH = 1                       # examples prepared ahead (2 measured no faster, and slower from host)
-    prefetch = {}                            # (pair index, from_host) -> prepared example
-
-    def prepared_step(i, from_host):
+    def prepared_step(self, i, from_host):
         """net.prepare(): voxelisation + index tables of ALL samples of step i on a side stream (the reference does
         its voxelisation ahead of time in DataLoader workers).  From host: the pinned scans are copied inside prepare()."""
-        src = host if from_host else resident
+        src = self.host if from_host else self.resident
         pts = []
-        for j in range(ppg):
-            a, b = src[(i * ppg + j) % pool_n]
+        for j in range(self.ppg):
+            a, b = src[(i * self.ppg + j) % self.pool_n]
             pts += [a, b]
             if from_host:
-                h2d_bytes[0] += a.numel() * 4 + b.numel() * 4
-        return net.prepare({"points": pts, "n_samples": ppg, "host_outputs": False})
+                self.h2d_bytes += a.numel() * 4 + b.numel() * 4
+        return self.net.prepare({"points": pts, "n_samples": self.ppg, "host_outputs": False})
 
-    def step(i, from_host):
+    def step(self, i, from_host):
         """one step = the ppg samples of the batch through ONE net(example) call (example["n_samples"] = ppg):
         loss = mean over the samples; one backward"""
-        if train:
-            reducer.zero_()
-            for c in image_caches:          # a real training step changes the weights: rebuild the split-TF32
+        torch, net = self.torch, self.net
+        if self.train:
+            self.reducer.zero_()
+            for c in self.image_caches:     # a real training step changes the weights: rebuild the split-TF32
                 c._c.clear()                # weight images once per step, as an optimizer step would force
-        ex = prefetch.pop((i, from_host), None)
+        ex = self.prefetch.pop((i, from_host), None)
         if ex is None:
-            ex = prepared_step(i, from_host)
-        if train:
+            ex = self.prepared_step(i, from_host)
+        if self.train:
             ret = net(ex)
             ret["loss"].sum().backward()
             res = ret["loss"].detach().reshape(-1)
@@ -274,81 +328,143 @@ def main():
             with torch.no_grad():
                 ret = net(ex)
             res = torch.cat([ret["translation_preds"], ret["rotation_preds"]], -1).reshape(-1)
-        # the next step's samples are prepared while this one's kernels run (the preparation's only host wait
-        # then happens with a whole step still queued on the main stream)
-        for stale in [k for k in prefetch if k[1] != from_host or k[0] <= i]:
-            del prefetch[stale]
-        for ahead in range(1, PREFETCH_DEPTH + 1):
-            if (i + ahead, from_host) not in prefetch:
-                prefetch[(i + ahead, from_host)] = prepared_step(i + ahead, from_host)
-        if train:
-            reducer.all_reduce()                    # pack into the flat buffer (+ NCCL all-reduce when N > 1)
+        # the next step's samples are prepared while this one's kernels run
+        for stale in [k for k in self.prefetch if k[1] != from_host or k[0] <= i]:
+            del self.prefetch[stale]
+        for ahead in range(1, self.PREFETCH_DEPTH + 1):
+            if (i + ahead, from_host) not in self.prefetch:
+                self.prefetch[(i + ahead, from_host)] = self.prepared_step(i + ahead, from_host)
+        if self.train:
+            self.reducer.all_reduce()               # pack into the flat buffer (+ NCCL all-reduce when N > 1)
         if from_host:
             r = res.cpu()                                                  # D2H of the step's result
-            d2h_bytes[0] += r.numel() * 4
+            self.d2h_bytes += r.numel() * 4
         return res
 
-    def timed(nsteps, from_host, first):
-        if world > 1:
+    def timed(self, nsteps, from_host, first):
+        """-> (total ms of exactly nsteps steps, max over ranks; per-step ms on this rank)"""
+        torch = self.torch
+        import torch.distributed as dist
+        if self.world > 1:
             dist.barrier()
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]
+        evs[0].record()
+        for i in range(nsteps):
+            self.flush.zero_()                                             # L2 flush between steps
+            self.step(first + i, from_host)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        ms = evs[0].elapsed_time(evs[-1])
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(nsteps)]
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, per
+
+    def quick(self, steps, warmup):
+        """pairs/s of this workload, device-resident inputs (used for the extras)"""
+        for i in range(warmup):
+            self.step(i, False)
+        ms, per = self.timed(steps, False, warmup)
+        per.sort()
+        return {"value": self.world * self.ppg * steps / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms / steps,
+                "ms_per_step_median": per[len(per) // 2], "steps": steps, "warmup": warmup}
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if xs else None
+
+
+def like_for_like_nn(dev):
+    """exact NN, 40000 x 40000 voxel means of a synthetic pair: own kernel (csrc/nn.cu) next to the reference's own
+    CUDA kernel compiled unmodified for sm_100a (oracle/_ref/cd_ref.so), same box, same inputs, results compared."""
+    import torch
+    from rslo_b200 import kernels as K
+    from rslo_b200.data import synthetic
+    import rslo_b200
+    so = os.path.join(ROOT, "oracle", "_ref", "cd_ref.so")
+    _, vg = rslo_b200.build_network(testing=False, seed=7)
+    a, b, _ = synthetic.make_pair(0)
+    pts = []
+    for s in (a, b):
+        out = K.voxelize(torch.from_numpy(s).to(dev), vg.voxel_size, vg.point_cloud_range, vg.grid_size, materialize=False)
+        n = int(out["n_dev"].item())
+        pts.append(out["mean"][:n, :3].contiguous())
+    n = min(p.shape[0] for p in pts)
+    q, t = pts[0][:n].contiguous(), pts[1][:n].contiguous()
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(nsteps):
-            flush.zero_()                                                  # L2 flush between steps
-            step(first + i, from_host)
+        for _ in range(reps):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return e0.elapsed_time(e1) / reps * 1e3
 
-    # warm-up (>= 3 steps), then the timed region
-    W = max(args.warmup, 3)
-    for i in range(W):
-        step(i, False)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = K.kernel_launch_count()
-    cuda_prof = os.environ.get("RSLO_BENCH_CUDA_PROFILER") == "1"      # ncu --profile-from-start off
-    if cuda_prof:
-        torch.cuda.profiler.start()
-    ms = timed(args.steps, False, W)
-    if cuda_prof:
-        torch.cuda.profiler.stop()
-    launches = K.kernel_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * ppg * args.steps / (ms / 1e3)
+    own_us = timeit(lambda: K.nn_exact(q, t), 50)
+    d_own, i_own = K.nn_exact(q, t)
+    out = {"n": int(n), "own_us": own_us, "reference_cuda_us": None, "bit_identical": None}
+    if os.path.exists(so):
+        try:
+            spec = importlib.util.spec_from_file_location("cd_ref", so)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            d = torch.zeros(1, n, device=dev)
+            i = torch.zeros(1, n, dtype=torch.int32, device=dev)
+            q1, t1 = q[None].contiguous(), t[None].contiguous()
+            out["reference_cuda_us"] = timeit(lambda: mod.forward_cuda_one_direction(q1, t1, d, i), 5)
+            out["bit_identical"] = bool(torch.equal(d[0], d_own) and torch.equal(i[0], i_own))
+            out["speedup"] = out["reference_cuda_us"] / own_us
+        except Exception as e:                      # the checker is optional on the box
+            out["reference_cuda_error"] = str(e)[:200]
+    else:
+        out["reference_cuda_error"] = "oracle/_ref/cd_ref.so not present"
+    return out
 
-    # e2e: host buffers -> net(example) -> host result
-    for i in range(2):
-        step(i, True)
-    h2d_bytes[0] = d2h_bytes[0] = 0
-    ms_e2e = timed(args.steps, True, W)
-    e2e = {"value": world * ppg * args.steps / (ms_e2e / 1e3), "unit": "pairs/s",
-           "h2d_bytes_per_step": h2d_bytes[0] // (args.steps + PREFETCH_DEPTH), "d2h_bytes_per_step": d2h_bytes[0] // args.steps,
-           "ms_per_step": ms_e2e / args.steps}
 
-    # roofline of the dominant kernel: profiled replica of the timed steps
-    roofline, breakdown = None, None
-    if not args.no_profile:                  # every rank runs the replica (its steps contain the collective)
-        K.PROFILE = []
-        nprof = min(args.steps, 5)
-        step(W, False)                       # fills the rulebook-size caches outside the measured calls
+def profile_replica(run, W, nprof):
+    """CUDA events around every C-ABI call of `nprof` steps (head un-graphed so its kernels are visible)."""
+    torch = run.torch
+    from rslo_b200 import kernels as K
+    from rslo_b200.models import odom_pred
+    cls = odom_pred.UNRResNetOdomPredEncDecSVDTempMask
+    saved = cls.use_cuda_graph
+    cls.use_cuda_graph = False
+    def plain_step(i):
+        # one stream only (no side-stream preparation): an event pair then brackets exactly the kernels of its call
+        if run.train:
+            run.reducer.zero_()
+            for c in run.image_caches:
+                c._c.clear()
+        pts = []
+        for j in range(run.ppg):
+            pts += list(run.resident[(i * run.ppg + j) % run.pool_n])
+        ex = {"points": pts, "n_samples": run.ppg, "host_outputs": False}
+        if run.train:
+            run.net(ex)["loss"].sum().backward()
+            run.reducer.all_reduce()
+        else:
+            with torch.no_grad():
+                run.net(ex)
+
+    try:
+        plain_step(W)                        # fills the rulebook-size caches outside the measured calls
         torch.cuda.synchronize()
         K.PROFILE = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(nprof):
-            flush.zero_()
-            step(W + i, False)
+            run.flush.zero_()
+            plain_step(W + 1 + i)
         e1.record()
         torch.cuda.synchronize()
         step_ms = e0.elapsed_time(e1) / nprof
@@ -359,45 +475,146 @@ def main():
             a[1] += s.elapsed_time(e)
             a[2] += nbytes
             a[3] += flops
+    finally:
         K.PROFILE = None
-    if not args.no_profile and rank == 0:
-        breakdown = {n: {"calls_per_step": a[0] / nprof, "ms_per_step": a[1] / nprof,
-                         "share_of_step": a[1] / nprof / step_ms,
-                         "algorithmic_GBps": a[2] / (a[1] * 1e-3) / 1e9 if a[1] > 0 else None}
-                     for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
-        breakdown["_step_ms_profiled"] = step_ms
-        dom = max(agg.items(), key=lambda kv: kv[1][1])
-        peak, peak_src = measured_peaks()
-        nm, a = dom
-        achieved = a[2] / (a[1] * 1e-3) / 1e9
-        roofline = {"kernel": nm, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": measured_traffic(nm), "peak_source": peak_src,
-                    "launches_per_step": a[0] / nprof, "avg_launch_ms": a[1] / a[0],
-                    "algorithmic_bytes_per_launch": a[2] / a[0], "gflops_per_launch": a[3] / a[0] / 1e9,
-                    "share_of_step": a[1] / nprof / step_ms,
-                    # the same launches seen as a contraction: useful FLOP/s (2*R*Cin*Cout); the split-TF32 scheme
-                    # executes 3x that on the tensor pipe (ncu: 32 % tensor-pipe active, smem-bandwidth bound)
-                    "useful_tflops": (a[3] / (a[1] * 1e-3) / 1e12) if a[1] > 0 else None,
-                    "note": "dominant OWN kernel by summed CUDA-event time; the cuDNN FP32 head is the larger share "
-                            "of the step (profiles/r01_launches_bench.md)"}
+        cls.use_cuda_graph = saved
+        run.prefetch.clear()
+    return agg, step_ms
+
+
+TENSOR_KERNELS = ("conv2d_tc", "conv2d_tc_wgrad")
+
+
+def roofline_of(name, a, nprof, ksum):
+    (hbm, hbm_src), (tf32, tf32_src) = measured_peaks()
+    common = {"kernel": name, "launches_per_step": a[0] / nprof, "avg_launch_ms": a[1] / a[0],
+              "algorithmic_bytes_per_launch": a[2] / a[0], "gflops_per_launch": a[3] / a[0] / 1e9,
+              "share_of_profiled_kernel_time": a[1] / nprof / ksum, "traffic": measured_traffic(name)}
+    if name in TENSOR_KERNELS:
+        ach = a[3] / (a[1] * 1e-3) / 1e12
+        common.update({"bound": "tensor", "achieved": ach, "peak": tf32, "unit": "TFLOP/s", "frac": ach / tf32,
+                       "peak_source": tf32_src,
+                       "note": "useful FLOPs 2*pixels*taps*Cin*Cout; the 3xTF32 operand split executes 3x that on the "
+                               "tensor pipe (executed fraction = 3 x frac)"})
+    else:
+        ach = a[2] / (a[1] * 1e-3) / 1e9
+        common.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                       "peak_source": hbm_src,
+                       "useful_tflops": (a[3] / (a[1] * 1e-3) / 1e12) if a[3] else None})
+    return common
+
+
+def main():
+    args = parse_args()
+    cfg = workload_config(args.workload, args.pairs_per_gpu, args.max_voxels)
+    if args.impl == "reference":
+        return reference_arm(args, cfg)
+
+    import torch
+    import torch.distributed as dist
+    from rslo_b200 import kernels as K
+    from rslo_b200.utils.distributed import init_from_env
+
+    rank, local, world = init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    run = Runner(cfg, dev, rank, world)
+    ppg = run.ppg
+    reducer_bytes = run.reducer.nbytes if (run.train and world > 1) else 0
+
+    # warm-up (>= 3 steps), then the timed region
+    W = max(args.warmup, 3)
+    for i in range(W):
+        run.step(i, False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = K.kernel_launch_count()
+    cuda_prof = os.environ.get("RSLO_BENCH_CUDA_PROFILER") == "1"      # ncu --profile-from-start off
+    if cuda_prof:
+        torch.cuda.profiler.start()
+    ms, per = run.timed(args.steps, False, W)
+    if cuda_prof:
+        torch.cuda.profiler.stop()
+    launches = K.kernel_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * ppg * args.steps / (ms / 1e3)
+
+    # e2e: host buffers -> net.prepare / net(example) -> host result
+    for i in range(3):
+        run.step(i, True)
+    run.h2d_bytes = run.d2h_bytes = 0
+    ms_e2e, per_e2e = run.timed(args.steps, True, W)
+    e2e = {"value": world * ppg * args.steps / (ms_e2e / 1e3), "unit": "pairs/s",
+           "h2d_bytes_per_step": run.h2d_bytes // (args.steps + run.PREFETCH_DEPTH),
+           "d2h_bytes_per_step": run.d2h_bytes // args.steps,
+           "ms_per_step": ms_e2e / args.steps, "ms_per_step_median": median(per_e2e)}
+
+    # rooflines: profiled replica of the timed steps (every rank runs it: its steps contain the collective)
+    roofline = roofline_hbm = breakdown = None
+    if not args.no_profile:
+        nprof = min(args.steps, 5)
+        agg, _ = profile_replica(run, W, nprof)
+        if rank == 0 and agg:
+            ksum = sum(a[1] for a in agg.values()) / nprof
+            breakdown = {n: {"calls_per_step": a[0] / nprof, "ms_per_step": a[1] / nprof,
+                             "share_of_profiled_kernel_time": a[1] / nprof / ksum,
+                             "algorithmic_GBps": a[2] / (a[1] * 1e-3) / 1e9 if a[1] > 0 else None,
+                             "useful_TFLOPs": a[3] / (a[1] * 1e-3) / 1e12 if (a[1] > 0 and a[3]) else None}
+                         for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+            breakdown["_profiled_kernel_ms_per_step"] = ksum
+            breakdown["_note"] = ("CUDA events around every C-ABI call of a replica of the timed steps with the head "
+                                  "un-graphed; the fused elementwise kernels of the head (BN/ReLU, tails) are not bracketed")
+            nm, a = max(agg.items(), key=lambda kv: kv[1][1])
+            roofline = roofline_of(nm, a, nprof, ksum)
+            hb = [(n, a) for n, a in agg.items() if n not in TENSOR_KERNELS]
+            if hb:
+                nm2, a2 = max(hb, key=lambda kv: kv[1][1])
+                roofline_hbm = roofline_of(nm2, a2, nprof, ksum)
     if world > 1:
         dist.barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _, _ = cpu_run(cfg, 2, 0, 40.0)
+        cpu_baseline, _, _, _ = cpu_run(cfg, 2, 0, 40.0)
+
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras and args.workload == "train":
+        extra = {}
+        del run
+        torch.cuda.empty_cache()
+        try:
+            extra["eval"] = dict(Runner(workload_config("eval"), dev, rank, world).quick(50, 10),
+                                 config=public_config(workload_config("eval")))
+            extra["train_warm"] = dict(Runner(workload_config("warm"), dev, rank, world).quick(30, 8),
+                                       config=public_config(workload_config("warm")))
+            torch.cuda.empty_cache()
+            sweep = {}
+            for nv in (40000, 80000, 160000, 250000):
+                c = workload_config("stress", max_voxels=nv)
+                r = Runner(c, dev, rank, world)
+                sweep[str(nv)] = r.quick(8, 4)
+                prep = r.net.prepare({"points": list(r.resident[0])})
+                sweep[str(nv)]["voxels_per_frame"] = [int(v.shape[0]) for v in prep["_prepared"]["frames"]["features"]]
+                del r, prep
+                torch.cuda.empty_cache()
+            extra["stress"] = {"config": public_config(workload_config("stress")), "max_voxels_sweep": sweep}
+            extra["like_for_like_nn"] = like_for_like_nn(dev)
+        except Exception as e:          # the extras never invalidate the headline line
+            extra["error"] = f"{type(e).__name__}: {e}"[:400]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": W,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": cfg["workload"], "mode": cfg["mode"], "pairs_per_gpu": ppg,
-                           "global_pairs_per_step": ppg * world, "parallelism": f"dp{world}",
-                           "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
-                                 f"{pool_n} distinct pairs per rank",
-                           "grad_allreduce_bytes": reducer.nbytes if (train and world > 1) else 0},
+                "ms_per_step": ms / args.steps, "ms_per_step_median": median(per), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": public_config(cfg, world, {
+                    "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
+                          f"{max(2 * ppg, 4)} distinct pairs per rank",
+                    "grad_allreduce_bytes": reducer_bytes}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown}
+                "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

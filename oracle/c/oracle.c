@@ -8,7 +8,7 @@
  * third-party fork DecaYale/spconv_plus (cloned unpinned, reference Dockerfile:58).  They are
  * restated here from the published spconv 1.x algorithm => "parity unpinned" for those rows
  * (SURVEY.md §8c).  The nearest-neighbour search restates code that IS in the reference tree and is
- * pinned against it (tests/test_oracle_pin.py, oracle/_ref).
+ * pinned against it (tests/test_cpu_oracle.py, oracle/_ref).
  *
  * Plain C99, no dependencies.  Built by oracle/build.py into oracle/_build/liboracle.so.
  */

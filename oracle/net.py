@@ -6,7 +6,7 @@ as the checker and as bench.py's cpu_baseline / --impl reference arm.
 TEST INFRASTRUCTURE ONLY — rslo_b200/ never imports this.
 
 Each function cites the reference code it follows; it is pinned against the reference's own Python
-(imported through oracle/ref_shim.py in the build container) by tests/test_oracle_pin.py and by the
+(imported through oracle/ref_shim.py in the build container) by tests/test_cpu_oracle.py and by the
 golden fixtures under tests/golden/ (made by tests/golden/make_golden.py from the REFERENCE net).
 The head / loss / tq-map rows are therefore pinned to reference code; the voxeliser, rulebook and
 sparse-conv rows restate the un-vendored spconv_plus fork => parity unpinned for those.

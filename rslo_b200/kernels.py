@@ -519,9 +519,9 @@ def conv2d_tc_prepare(weight_oihw, mode, out=None, cout_padded=None):
     return out
 
 
-def _cost_conv2d(out, x_split, image, cout, ksize, stride, *a, **k):
+def _cost_conv2d(res_, x_split, image, cout, ksize, stride, *a, **k):
     _, B, H, W, cin = x_split.shape
-    npx = out.shape[0] * out.shape[1] * out.shape[2]
+    npx = res_.shape[0] * res_.shape[1] * res_.shape[2]
     return 4 * (B * H * W * cin + npx * cout + ksize * ksize * cin * cout), 2 * npx * ksize * ksize * cin * cout
 
 
@@ -543,13 +543,13 @@ def conv2d_tc_forward(x_split, image, cout, ksize, stride, bias=None, relu=False
     return out
 
 
-def _cost_conv2d_bwd(out, g_split, image_t, in_shape, ksize, stride, *a, **k):
+def _cost_conv2d_bwd(res_, g_split, image_t, in_shape, ksize, stride, *a, **k):
     _, B, Ho, Wo, cout = g_split.shape
     _, H, W, cin = in_shape
     return 4 * (B * H * W * cin + B * Ho * Wo * cout + ksize * ksize * cin * cout), 2 * B * Ho * Wo * ksize * ksize * cin * cout
 
 
-@_profiled("conv2d_tc_dgrad", _cost_conv2d_bwd)
+@_profiled("conv2d_tc", _cost_conv2d_bwd)          # same CUDA kernel (k_conv2d_tc) as the forward, other tap table
 def conv2d_tc_backward_data(g_split, image_t, in_shape, ksize, stride, out=None, accumulate=False):
     """dx [B,H,W,Cin] (= or +=) from g_split [2,B,Ho,Wo,Cout] and the mode-1 weight image."""
     g = _f32(g_split)
@@ -566,7 +566,7 @@ def conv2d_tc_backward_data(g_split, image_t, in_shape, ksize, stride, out=None,
     return out
 
 
-def _cost_conv2d_wgrad(out, x_split, g_split, ksize, stride, *a, **k):
+def _cost_conv2d_wgrad(res_, x_split, g_split, ksize, stride, *a, **k):
     _, B, H, W, cin = x_split.shape
     _, _, Ho, Wo, cout = g_split.shape
     return 4 * (B * H * W * cin + B * Ho * Wo * cout + ksize * ksize * cin * cout), 2 * B * Ho * Wo * ksize * ksize * cin * cout

@@ -149,6 +149,7 @@ class UnVoxelOdomNetICP3(nn.Module):
         self.register_buffer("global_step", torch.LongTensor(1).zero_())
         self._step_host = None          # host mirror of global_step: no device read per query
         self.warm_flag = False
+        self.__dict__["on_head_backward_done"] = None      # optional callback, see utils/distributed.FlatGradAllReducer
         self._time_dict, self._time_total_dict, self._time_count_dict = {}, {}, {}
 
     # ---- bookkeeping (voxel_odom_net.py:206-287) -------------------------------------------------
@@ -293,6 +294,11 @@ class UnVoxelOdomNetICP3(nn.Module):
             head_in = spatial_features
         else:       # frame slot t of every sample -> one [S,C,H,W] batch: all pairs of all samples in one head pass
             head_in = [torch.cat([spatial_features[s * T + t] for s in range(S)], dim=0) for t in range(T)]
+        cb = self.__dict__.get("on_head_backward_done")
+        if cb is not None and torch.is_grad_enabled() and head_in[0].requires_grad:
+            # fires when autograd reaches the head's input, i.e. right after the head's backward has produced (and
+            # accumulated) every head parameter gradient: lets a gradient reducer start on them early
+            head_in[0].register_hook(lambda g, _cb=cb: (_cb(), g)[1])
         preds_dict = self.odom_predictor(head_in, tq_map_gt=None)
         if self.training or self.testing:
             with torch.no_grad():

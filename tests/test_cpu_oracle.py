@@ -199,6 +199,29 @@ def test_oracle_matches_reference_live():
                                rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (build container only)")
+def test_our_builders_accept_the_reference_protobuf_message():
+    """Drop-in boundary: rslo_b200's voxel_builder / second_builder take the reference's REAL protobuf message
+    (`pipeline_pb2.TrainEvalPipelineConfig().model.second` parsed by google.protobuf from the reference's own prototxt)
+    exactly as `train_hdf5.py:92-101` passes it, and build a net with the reference's state_dict keys and shapes."""
+    ref_shim.install()
+    from google.protobuf import text_format
+    from rslo.protos import pipeline_pb2                      # the reference's generated module
+    from rslo_b200.builder import second_builder, voxel_builder
+    cfg = pipeline_pb2.TrainEvalPipelineConfig()
+    with open("/root/reference/config/kitti_train_ours.prototxt") as f:
+        text_format.Merge(f.read(), cfg)
+    vg = voxel_builder.build(cfg.model.second.voxel_generator)
+    assert vg.grid_size.tolist() == [1408, 768, 40]
+    net = second_builder.build(cfg.model.second, vg, measure_time=False, testing=False)
+    rnet, _ = ref_shim.build_reference_net("/root/reference/config/kitti_train_ours.prototxt", testing=False, seed=7)
+    ours = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    theirs = {k: tuple(v.shape) for k, v in rnet.state_dict().items()}
+    assert ours == theirs
+    assert net.icp_iter == rnet.icp_iter and net._pyloss_exp_w_base == rnet._pyloss_exp_w_base
+    assert float(net._rotation_loss.alpha) == float(rnet._rotation_loss.alpha)
+
+
 def test_quaternion_conversions_vs_scipy():
     """kornia 0.4.0 is not vendored (parity unpinned): cross-check the restatement against an independent
     implementation (scipy Rotation, same x,y,z,w convention), incl. the four branches of the matrix->quaternion
