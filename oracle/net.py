@@ -349,18 +349,28 @@ def loss_forward(sd, head, voxel_features, cov_preds, step, icp_iter_cfg=2, pc_r
 # ------------------------------------------------------------------------------------------------
 # whole path
 # ------------------------------------------------------------------------------------------------
-def encode_frame(sd, points, training=False, max_voxels=40000):
-    vox = native.voxelize(points, VS, RANGE, 10, max_voxels, 1, 8, -1.0)
+def sparse_shape_of(voxel_size):
+    """grid (x,y,z) = round(range / voxel_size); sparse shape (z+1, y, x)  (`voxel_builder.py`, `middle.py:111`)"""
+    r = np.asarray(RANGE, np.float64)
+    g = np.round((r[3:] - r[:3]) / np.asarray(voxel_size, np.float64)).astype(np.int64)
+    return [int(g[2]) + 1, int(g[1]), int(g[0])]
+
+
+def encode_frame(sd, points, training=False, max_voxels=40000, voxel_size=None):
+    vs = VS if voxel_size is None else list(voxel_size)
+    shape = SPARSE_SHAPE if voxel_size is None else sparse_shape_of(vs)
+    vox = native.voxelize(points, vs, RANGE, 10, max_voxels, 1, 8, -1.0)
     feat = sparse.vfe_mean(vox["voxels"], vox["num_points_per_voxel"])
     n = feat.shape[0]
     coors = np.concatenate([np.zeros((n, 1), np.int32), vox["coordinates"]], 1)
-    bev, cov, tables = sparse.middle_forward(sd, feat, coors, SPARSE_SHAPE, training=training)
+    bev, cov, tables = sparse.middle_forward(sd, feat, coors, shape, training=training)
     return feat, bev, cov, vox, tables
 
 
-def pair_forward(sd, frames, training=False, step=2000, with_loss=None, grads_for=()):
+def pair_forward(sd, frames, training=False, step=2000, with_loss=None, grads_for=(), voxel_size=None, max_voxels=40000):
     """frames: list of T point arrays [P,7].  Returns dict(pose [B,7], loss terms, maps...).
-    `grads_for`: state_dict keys whose d(loss)/d(param) to return (training only)."""
+    `grads_for`: state_dict keys whose d(loss)/d(param) to return (training only).
+    `voxel_size` / `max_voxels`: other than the shipped 0.1 x 0.1 x 0.2 m / 40000 (dense-scan stress configuration)."""
     sd = dict(sd)
     for k in grads_for:
         sd[k] = sd[k].clone().requires_grad_(True)
@@ -369,7 +379,7 @@ def pair_forward(sd, frames, training=False, step=2000, with_loss=None, grads_fo
     with ctx:
         feats, bevs, covs, n_vox = [], [], [], []
         for pts in frames:
-            f, bev, cov, vox, _ = encode_frame(sd, pts, training)
+            f, bev, cov, vox, _ = encode_frame(sd, pts, training, max_voxels=max_voxels, voxel_size=voxel_size)
             feats.append(f); bevs.append(bev); covs.append(cov); n_vox.append(f.shape[0])
         head = head_forward(sd, bevs, training)
         out = {"pose": torch.cat([head["translation_preds"], head["rotation_preds"]], -1).detach().numpy(),
