@@ -54,6 +54,11 @@ def parse_args():
     return ap.parse_args()
 
 
+# optimizer of kitti_train_ours.prototxt:146-158 at the first step of its one-cycle schedule (lr_max 0.8e-3 / div_factor 10,
+# moms[0] 0.95, betas[1] 0.99 with fixed_weight_decay, weight_decay 1e-5) + train_hdf5.py:671 clip at 10
+OPT = {"lr": 0.8e-4, "mom": 0.95, "beta": 0.99, "eps": 1e-8, "wd": 1e-5, "max_norm": 10.0}
+
+
 def workload_config(workload, pairs_per_gpu=None, max_voxels=None):
     if workload == "eval":
         return {"workload": "C2 eval fwd: 120k-pt pair (64 beams x 1875 az), voxel 0.1x0.1x0.2 m, <=40000 voxels/frame, "
@@ -135,10 +140,22 @@ def cpu_run(cfg, steps, warmup, budget_s):
     ppg = cfg["pairs_per_gpu"]
     pairs = make_pairs(max(2, ppg), cfg["beams"], cfg["n_az"], 100)
 
+    from oracle import optim as oopt
+    opt_state = oopt.new_state([sd[k] for k in keys]) if train else None
+
     def one_step(i):
+        acc = None
         for j in range(ppg):
-            onet.pair_forward(sd, list(pairs[(i * ppg + j) % len(pairs)]), training=train, step=cfg["global_step"],
-                              grads_for=keys)
+            out = onet.pair_forward(sd, list(pairs[(i * ppg + j) % len(pairs)]), training=train, step=cfg["global_step"],
+                                    grads_for=keys)
+            if train:
+                gs = [None if out["grads"][k] is None else torch.from_numpy(out["grads"][k]) / ppg for k in keys]
+                acc = gs if acc is None else [b if a is None else (a if b is None else a + b) for a, b in zip(acc, gs)]
+        if train:           # clip_grad_norm_(10) + OptimWrapper.step() (true weight decay + Adam), as train_hdf5.py:671-672
+            _, clipped = oopt.clip_grad_norm(acc, OPT["max_norm"])
+            with torch.no_grad():
+                oopt.adam_step([sd[k] for k in keys], clipped, opt_state, OPT["lr"], OPT["mom"], OPT["beta"], OPT["eps"],
+                               wd=OPT["wd"], true_wd=True)
 
     t_all0 = time.time()
     w_done = 0
@@ -287,14 +304,18 @@ class Runner:
         net._step_host = None
         net.train(self.train)
         self.net, self.vg = net, vg
-        self.reducer = FlatGradAllReducer(net) if self.train else None
+        self.reducer = self.opt = None
+        if self.train:
+            from rslo_b200.torchplus.train import FusedAdamClip
+            self.reducer = FlatGradAllReducer(net, early_module=net.odom_predictor)
+            self.opt = FusedAdamClip(self.reducer, lr=OPT["lr"], wd=OPT["wd"], true_wd=True, betas=(OPT["mom"], OPT["beta"]),
+                                     eps=OPT["eps"], max_norm=OPT["max_norm"])
         self.pool_n = max(2 * self.ppg, 4)
         pairs = make_pairs(self.pool_n, cfg["beams"], cfg["n_az"], first_seed=1000 * rank)
         self.host = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
         self.resident = [(a.to(dev), b.to(dev)) for a, b in self.host]
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
         self.h2d_bytes = self.d2h_bytes = 0
-        self.image_caches = [m._images for m in net.modules() if hasattr(m, "_images")]
         self.prefetch = {}
 
     def prepared_step(self, i, from_host):
@@ -315,8 +336,6 @@ class Runner:
         torch, net = self.torch, self.net
         if self.train:
             self.reducer.zero_()
-            for c in self.image_caches:     # a real training step changes the weights: rebuild the split-TF32
-                c._c.clear()                # weight images once per step, as an optimizer step would force
         ex = self.prefetch.pop((i, from_host), None)
         if ex is None:
             ex = self.prepared_step(i, from_host)
@@ -335,7 +354,8 @@ class Runner:
             if (i + ahead, from_host) not in self.prefetch:
                 self.prefetch[(i + ahead, from_host)] = self.prepared_step(i + ahead, from_host)
         if self.train:
-            self.reducer.all_reduce()               # pack into the flat buffer (+ NCCL all-reduce when N > 1)
+            self.reducer.all_reduce(average=False)  # pack into the flat buffer (+ NCCL all-reduce when N > 1)
+            self.opt.step()                         # global-norm clip + 1/world + weight decay + Adam: 2 launches
         if from_host:
             r = res.cpu()                                                  # D2H of the step's result
             self.d2h_bytes += r.numel() * 4
@@ -443,15 +463,14 @@ def profile_replica(run, W, nprof):
         # one stream only (no side-stream preparation): an event pair then brackets exactly the kernels of its call
         if run.train:
             run.reducer.zero_()
-            for c in run.image_caches:
-                c._c.clear()
         pts = []
         for j in range(run.ppg):
             pts += list(run.resident[(i * run.ppg + j) % run.pool_n])
         ex = {"points": pts, "n_samples": run.ppg, "host_outputs": False}
         if run.train:
             run.net(ex)["loss"].sum().backward()
-            run.reducer.all_reduce()
+            run.reducer.all_reduce(average=False)
+            run.opt.step()
         else:
             with torch.no_grad():
                 run.net(ex)
@@ -539,6 +558,7 @@ def main():
     if cuda_prof:
         torch.cuda.profiler.stop()
     launches = K.kernel_launch_count() - l0
+    run_train = run.train
     clocks = sampler.stop() if rank == 0 else None
     value = world * ppg * args.steps / (ms / 1e3)
 
@@ -612,7 +632,9 @@ def main():
                 "config": public_config(cfg, world, {
                     "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
                           f"{max(2 * ppg, 4)} distinct pairs per rank",
-                    "grad_allreduce_bytes": reducer_bytes}),
+                    "grad_allreduce_bytes": reducer_bytes,
+                    "optimizer": ("every train step ends with clip_grad_norm 10 + true weight decay + Adam (fused, 2 launches; "
+                                  f"lr {OPT['lr']}, betas ({OPT['mom']}, {OPT['beta']}), wd {OPT['wd']})") if run_train else None}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "extra": extra}
         print(json.dumps(line), flush=True)

@@ -335,6 +335,36 @@ int rslo_cov_residual_backward(const float* pred, const float* target, const int
                                const float* grad_loss, float* grad_pred, float* grad_target, float* grad_cov_pred,
                                float* grad_cov_target, rslo_stream_t stream);
 
+/* ---- f-N2: the optimizer step in two launches (csrc/optim.cu) --------------------------------------------
+ * Replaces torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0) (train_hdf5.py:671) followed by
+ * OptimWrapper.step() (rslo/torchplus/train/fastai_optim.py:181-194: p *= 1 - wd*lr on every trainable parameter,
+ * then torch.optim.Adam(betas=(mom, 0.99)).step(), rslo/builder/optimizer_builder.py:101-118) over the flat gradient
+ * buffer the all-reduce already uses.
+ * rslo_grad_sumsq: *sumsq_out = sum of squares of grad[0..n) in double, bit-reproducible (fixed combine order).
+ *   workspace: rslo_grad_norm_workspace_bytes() bytes, ZEROED once by the caller (the kernel leaves it zeroed).
+ * rslo_adam_step: one CTA per chunk; chunk = up to a few thousand contiguous elements of ONE parameter:
+ *   p = first element of the chunk in the parameter's own storage, off = its offset in grad / exp_avg / exp_avg_sq,
+ *   flags bit 0 = the parameter received a gradient this step (otherwise only the weight decay is applied, as
+ *   torch's Adam skips parameters whose .grad is None).
+ *   g' = grad_scale * grad (grad_scale = 1 / world_size folds the all-reduce average in); when sumsq != NULL and
+ *   max_norm > 0 the clip coefficient min(1, max_norm / (grad_scale * sqrt(*sumsq) + 1e-6)) multiplies g';
+ *   true_wd != 0: p *= 1 - weight_decay * lr, else g' += weight_decay * p (Adam's L2);
+ *   m = m + (1-beta1)(g'-m); v = beta2 v + (1-beta2) g'^2; p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).
+ *   write_clipped_grad != 0 stores g' back into grad (what clip_grad_norm_ leaves behind). */
+typedef struct {
+    float* p;
+    unsigned int off;
+    unsigned int n;
+    unsigned int flags;
+    unsigned int reserved;
+} rslo_adam_chunk_t;
+size_t rslo_grad_norm_workspace_bytes(void);
+int rslo_grad_sumsq(const float* grad, size_t n, double* sumsq_out, void* workspace, size_t workspace_bytes,
+                    rslo_stream_t stream);
+int rslo_adam_step(const rslo_adam_chunk_t* chunks_dev, int n_chunks, float* grad, float* exp_avg, float* exp_avg_sq,
+                   const double* sumsq, float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int true_wd, int step, int write_clipped_grad, rslo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

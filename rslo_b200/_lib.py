@@ -83,6 +83,9 @@ SIGNATURES = {
     "rslo_cov_residual_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp]),
     "rslo_dense_backward": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "rslo_grad_norm_workspace_bytes": (_sz, []),
+    "rslo_grad_sumsq": (_i, [_vp, _sz, _vp, _vp, _sz, _vp]),
+    "rslo_adam_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _vp]),
 }
 
 
@@ -101,6 +104,10 @@ def _bind():
 
 
 _bind()
+
+
+class AdamChunk(C.Structure):            # rslo_adam_chunk_t
+    _fields_ = [("p", C.c_void_p), ("off", C.c_uint), ("n", C.c_uint), ("flags", C.c_uint), ("reserved", C.c_uint)]
 
 
 class RsloError(RuntimeError):

@@ -1,6 +1,6 @@
 // Elementwise / reduction companions of the dense tensor-core convolutions (conv2d_tc.cu): everything the
 // odometry head does BETWEEN its convolutions, in the layout the convolutions consume (NHWC rows, stored as the
-// split pair hi = RN_tf32(x), lo = x - hi) so no activation is ever re-laid-out or re-split by a separate pass.
+// split pair hi = RN_tf32(x), lo = RN_tf32(x - hi)) so no activation is ever re-laid-out or re-split by a separate pass.
 //
 //   k_head_pack / k_head_unpack : NCHW BEV maps of a frame pair <-> NHWC split pair (+ first-frame occupancy mask,
 //                                 `rslo/models/odom_pred.py:165-168`)
@@ -26,7 +26,7 @@ constexpr int HE_THREADS = 256;
 __device__ __forceinline__ void split4(const float4& v, float4& h, float4& l)
 {
     h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-    l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    l = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -58,7 +58,7 @@ __global__ void k_head_pack(const float* __restrict__ x1, const float* __restric
                 const float h = tf32_rn(v);
                 const size_t o = ((size_t)b * HW + p) * C2 + ct * 32 + tx;
                 hi[o] = h;
-                lo[o] = v - h;
+                lo[o] = tf32_rn(v - h);
             }
         }
         __syncthreads();
@@ -399,14 +399,14 @@ __global__ void k_multi_prepare(const rslo_conv_prep_t* __restrict__ tab)
             const float v = co < e.Cout ? __ldg(e.w + ((size_t)co * e.Cin + ci) * e.taps + t) : 0.f;
             const float h = tf32_rn(v);
             e.img_fwd[i] = h;
-            e.img_fwd[(size_t)total + i] = v - h;
+            e.img_fwd[(size_t)total + i] = tf32_rn(v - h);
         }
         if (e.img_bwd) {                        // [t][ci][co]
             const int ci = r / e.CoutP, co = r - ci * e.CoutP;
             const float v = co < e.Cout ? __ldg(e.w + ((size_t)co * e.Cin + ci) * e.taps + t) : 0.f;
             const float h = tf32_rn(v);
             e.img_bwd[i] = h;
-            e.img_bwd[(size_t)total + i] = v - h;
+            e.img_bwd[(size_t)total + i] = tf32_rn(v - h);
         }
     }
     if (e.bias_pad && blockIdx.x == 0)

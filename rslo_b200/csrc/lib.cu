@@ -12,7 +12,7 @@ void set_last_error(const char* what, cudaError_t e)
 }
 }  // namespace rslo
 
-extern "C" int rslo_abi_version(void) { return 3; }   // 3: dense head (conv2d_tc, head_ops); 2: rslo_kabsch gained tgt_idx + normal; tensor-core entry points
+extern "C" int rslo_abi_version(void) { return 4; }   // 4: optimizer step (optim.cu); 3: dense head (conv2d_tc, head_ops); 2: rslo_kabsch gained tgt_idx + normal; tensor-core entry points
 extern "C" const char* rslo_last_error(void) { return rslo::g_err; }
 
 extern "C" unsigned long long rslo_kernel_launch_count(void) { return rslo::g_launch_count; }

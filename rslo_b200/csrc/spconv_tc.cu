@@ -212,7 +212,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 const float4 hh = v[j], ll = v[j];
 #else
                 const float4 hh = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
-                const float4 ll = make_float4(v[j].x - hh.x, v[j].y - hh.y, v[j].z - hh.z, v[j].w - hh.w);
+                const float4 ll = make_float4(tf32_rn(v[j].x - hh.x), tf32_rn(v[j].y - hh.y), tf32_rn(v[j].z - hh.z), tf32_rn(v[j].w - hh.w));
 #endif
                 sts128(stage + soff[j], hh);
                 sts128(stage + S::A_BYTES + soff[j], ll);

@@ -134,7 +134,7 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (o < row_end) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)o * COUT) + c);
                     const float4 hh = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-                    const float4 ll = make_float4(v.x - hh.x, v.y - hh.y, v.z - hh.z, v.w - hh.w);
+                    const float4 ll = make_float4(tf32_rn(v.x - hh.x), tf32_rn(v.y - hh.y), tf32_rn(v.z - hh.z), tf32_rn(v.w - hh.w));
                     const uint32_t off = mn32_offset(r, c * 4, WG_STEP);
                     sts128(base + off, hh);
                     sts128(base + C::G_BYTES + off, ll);
@@ -168,7 +168,7 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
                     const int i = tid + j * WG_PRODUCERS;
                     const int r = i / CH, c = i % CH;
                     const float4 hh = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
-                    const float4 ll = make_float4(v[j].x - hh.x, v[j].y - hh.y, v[j].z - hh.z, v[j].w - hh.w);
+                    const float4 ll = make_float4(tf32_rn(v[j].x - hh.x), tf32_rn(v[j].y - hh.y), tf32_rn(v[j].z - hh.z), tf32_rn(v[j].w - hh.w));
                     const uint32_t off = mn32_offset(r, c * 4, WG_STEP);
                     sts128(base + off, hh);
                     sts128(base + C::A_BYTES + off, ll);

@@ -662,3 +662,38 @@ def upcat_backward(dcat, shape, up, ld, choff, dz, accumulate):
 def bias_grad(g, n_rows, ld, c, out):
     check(lib.rslo_bias_grad(ptr(g), n_rows, ld, c, ptr(out), stream()), "rslo_bias_grad")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# f-N2: optimizer step (csrc/optim.cu)
+# ------------------------------------------------------------------------------------------------
+def grad_norm_workspace_bytes():
+    return int(lib.rslo_grad_norm_workspace_bytes())
+
+
+def _cost_sumsq(res_, flat, *a, **k):
+    return 4 * flat.numel(), 2 * flat.numel()
+
+
+@_profiled("grad_sumsq", _cost_sumsq)
+def grad_sumsq(flat, out, ws):
+    """out[0] (float64) = sum of squares of the flat fp32 gradient buffer (bit-reproducible); ws: zeroed once."""
+    assert flat.dtype == torch.float32 and flat.is_cuda and flat.is_contiguous() and out.dtype == torch.float64
+    check(lib.rslo_grad_sumsq(ptr(flat), flat.numel(), ptr(out), ptr(ws), ws.numel(), stream()), "rslo_grad_sumsq")
+    _count()
+    return out
+
+
+def _cost_adam(res_, table, n_chunks, flat, *a, **k):
+    return 28 * flat.numel(), 12 * flat.numel()
+
+
+@_profiled("adam_step", _cost_adam)
+def adam_step(table, n_chunks, flat, exp_avg, exp_avg_sq, sumsq, grad_scale, max_norm, lr, beta1, beta2, eps,
+              weight_decay, true_wd, step, write_clipped_grad=False):
+    """clip coefficient + 1/world scaling + weight decay + Adam over every chunk of `table` (rslo_adam_chunk_t[])."""
+    check(lib.rslo_adam_step(ptr(table), n_chunks, ptr(flat), ptr(exp_avg), ptr(exp_avg_sq), ptr(sumsq),
+                             float(grad_scale), float(max_norm), float(lr), float(beta1), float(beta2), float(eps),
+                             float(weight_decay), 1 if true_wd else 0, int(step), 1 if write_clipped_grad else 0,
+                             stream()), "rslo_adam_step")
+    _count()

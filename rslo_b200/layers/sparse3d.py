@@ -120,16 +120,28 @@ class _DenseFramesFn(torch.autograd.Function):
         return grad, None
 
 
+_IMAGE_GENERATION = [0]
+
+
+def invalidate_weight_images():
+    """Forget every cached weight image.  In-place writes through `.data` / raw pointers (the reference's optimizer
+    wrapper `p.data.mul_`, `model.data.copy_(master)`, NCCL broadcasts, this repo's fused Adam kernel) do not advance
+    a tensor's version counter, so the network calls this at the start of every training forward (weights change
+    every step anyway: an image is never reused across steps) and after load_state_dict / optimizer steps."""
+    _IMAGE_GENERATION[0] += 1
+
+
 class _ImageCache:
-    """Pre-swizzled split-TF32 weight images of one layer (csrc/spconv_tc.cu), rebuilt only when the weight
-    changes (tensor version counter): the frames / pairs of a step share them."""
+    """Pre-swizzled split-TF32 weight images of one layer (csrc/spconv_tc.cu), rebuilt when the weight changes
+    (tensor version counter, storage address, or `invalidate_weight_images()`): the frames / pairs of a step and
+    consecutive eval calls share them."""
 
     def __init__(self):
         self._c = {}
 
     def get(self, weight, transpose, mirror):
         key = (bool(transpose), bool(mirror))
-        ver = (weight._version, weight.data_ptr())
+        ver = (weight._version, weight.data_ptr(), _IMAGE_GENERATION[0])
         hit = self._c.get(key)
         if hit is None or hit[0] != ver:
             hit = (ver, K.spconv_tc_prepare(weight.detach(), transpose=transpose, mirror=mirror))

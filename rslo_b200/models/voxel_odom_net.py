@@ -22,6 +22,7 @@ from torch.nn import functional as F
 from .. import kernels as K
 from ..data.dataset import generate_pointwise_local_transformation_tch
 from ..layers.pose_tail import loss_geometry, loss_tail
+from ..layers.sparse3d import invalidate_weight_images
 from ..torchplus import roll
 from ..utils import pose_utils
 from . import middle, odom_pred, voxel_encoder
@@ -314,6 +315,8 @@ class UnVoxelOdomNetICP3(nn.Module):
         return preds_dict
 
     def forward(self, example):
+        if self.training:
+            invalidate_weight_images()      # weights move every step, possibly through .data
         if "_prepared" in example:
             prep = example["_prepared"]
             torch.cuda.current_stream().wait_event(prep["event"])

@@ -69,6 +69,8 @@ class FlatGradAllReducer:
         self._comm = None
         self._early_work = None
         self._early_done = False
+        self.present = [False] * len(self.params)       # which parameters received a gradient (recorded by pack)
+        self._packed = False
         if early_module is not None and self.world > 1 and ref.is_cuda and hasattr(module, "on_head_backward_done"):
             self._comm = torch.cuda.Stream(device=ref.device)
             module.on_head_backward_done = self._reduce_early
@@ -82,6 +84,8 @@ class FlatGradAllReducer:
             p.grad = None
         self._early_done = False
         self._early_work = None
+        self._packed = False
+        self.pending_average = False
 
     def broadcast_params(self, src=0):
         """Same replica everywhere: parameters AND buffers (BatchNorm running statistics, global_step)
@@ -106,14 +110,17 @@ class FlatGradAllReducer:
                     dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)
                     b.div_(self.world)
 
-    def _pack(self, params, views):
+    def _pack(self, params, views, first=0):
         """Gradients -> flat buffer slices (one multi-tensor copy); `p.grad` becomes the slice.  Slices of parameters
         without a gradient are zeroed individually (gradients that already live in their slices stay untouched)."""
         src, dst, missing = [], [], []
-        for p, v in zip(params, views):
+        for i, (p, v) in enumerate(zip(params, views)):
             if p.grad is None:
                 missing.append(v)
-            elif p.grad.data_ptr() != v.data_ptr():
+                self.present[first + i] = False
+                continue
+            self.present[first + i] = True
+            if p.grad.data_ptr() != v.data_ptr():
                 src.append(p.grad)
                 dst.append(v)
         if missing:
@@ -125,9 +132,12 @@ class FlatGradAllReducer:
 
     def pack(self):
         ne = len(self.early)
+        if self._packed:            # a second pack of the same step would mark the zero-filled slices as gradients
+            return self.flat
         if not self._early_done:
             self._pack(self.early, self.views[:ne])
-        self._pack(self.rest, self.views[ne:])
+        self._pack(self.rest, self.views[ne:], ne)
+        self._packed = True
         return self.flat
 
     def _reduce_early(self):
@@ -143,8 +153,12 @@ class FlatGradAllReducer:
             self._early_work = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._early_done = True
 
-    def all_reduce(self):
-        """sum -> average over ranks, in place; one NCCL call per bucket (the early bucket may already be in flight)."""
+    pending_average = False
+
+    def all_reduce(self, average=True):
+        """sum -> average over ranks, in place; one NCCL call per bucket (the early bucket may already be in flight).
+        average=False leaves the SUM in the buffer and sets `pending_average`: the fused optimizer step
+        (torchplus/train/fused_optim.py) folds the 1/world factor into its own pass over the gradients."""
         self.pack()
         if self.world > 1:
             if self._early_done:
@@ -155,5 +169,8 @@ class FlatGradAllReducer:
                 self._early_work = None
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(self.world)
+            if average:
+                self.flat.div_(self.world)
+            else:
+                self.pending_average = True
         return self.flat

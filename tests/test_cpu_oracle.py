@@ -239,3 +239,40 @@ def test_quaternion_conversions_vs_scipy():
     q_ref = Rotation.from_matrix(R_ref).as_quat()
     sgn = np.sign(np.sum(q_back * q_ref, axis=1, keepdims=True))
     np.testing.assert_allclose(q_back * sgn, q_ref, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (build container only)")
+def test_optimizer_oracle_matches_reference_live():
+    """f-N2 pin: oracle/optim.py (clip + true weight decay + Adam + one-cycle) against the reference's own
+    OptimWrapper / OneCycle classes driving torch.optim.Adam, three steps, one parameter without gradient."""
+    from functools import partial
+    from oracle import optim as oopt
+    ref_shim.install()
+    from rslo.torchplus.train.fastai_optim import OptimWrapper
+    from rslo.torchplus.train.learning_schedules_fastai import OneCycle
+    g = torch.Generator().manual_seed(5)
+    mods = torch.nn.ModuleList([torch.nn.Linear(7, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2)])
+    for p in mods.parameters():
+        p.data = torch.randn(p.shape, generator=g)
+    opt = OptimWrapper.create(partial(torch.optim.Adam, betas=(0.9, 0.99), amsgrad=False), 3e-3,
+                              [[torch.nn.ModuleList(list(mods)[:2])], [torch.nn.ModuleList(list(mods)[2:])]],   # as
+                              wd=1e-2, true_wd=True, bn_wd=True)     # get_voxeLO_net_layer_groups: a list of [ModuleList]
+    sched = OneCycle(opt, 40, 0.8e-3, [0.95, 0.85], 10.0, 0.05)
+    # the wrapper orders parameters by (non-BN, BN) group: follow torch's own order for the comparison
+    params_ref = list(mods.parameters())
+    params = [p.detach().clone() for p in params_ref]
+    state = oopt.new_state(params)
+    for step in range(3):
+        grads = [torch.randn(p.shape, generator=g) * 30 for p in params_ref]
+        grads[-1] = None                                    # last bias: no gradient this step
+        for p, gr in zip(params_ref, grads):
+            p.grad = None if gr is None else gr.clone()
+        sched.step(step)
+        lr, mom = oopt.one_cycle(step, 40, 0.8e-3, [0.95, 0.85], 10.0, 0.05)
+        assert abs(opt.lr - lr) < 1e-12 and abs(opt.mom - mom) < 1e-12
+        torch.nn.utils.clip_grad_norm_(params_ref, 10.0)
+        opt.step()
+        _, clipped = oopt.clip_grad_norm(grads, 10.0)
+        oopt.adam_step(params, clipped, state, lr, mom, 0.99, 1e-8, wd=1e-2, true_wd=True)
+        for a, b in zip(params, params_ref):
+            assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-7)

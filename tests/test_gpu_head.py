@@ -3,11 +3,16 @@ against the same module tree evaluated by torch in FLOAT64 (`_trunk_torch`, the 
 `rslo/models/odom_pred.py:152-260`): outputs, input gradients, every parameter gradient, BatchNorm running
 statistics; training mode with per-sample statistics groups, frozen-BN mode and eval mode.
 Tolerances.  Forward outputs: 2e-5 of the tensor's max magnitude (split-TF32 products are FP32-level; measured
-1e-7 .. 6e-6).  Gradients: backpropagation through ~35 BatchNorm + ReLU layers with random weights amplifies
-rounding noise by ~1e4 (torch's own FP32/cuDNN evaluation of the same trunk is 1e-3 .. 7e-3 away from float64,
-measured on B200), so each gradient's relative L2 error is bounded by a multiple of the error that torch-FP32
-shows on the same tensor (the reference's arithmetic), with an absolute floor.  The formulas themselves are pinned
-tightly by the kernel-level tests below (1e-5 on well-conditioned inputs)."""
+1e-7 .. 3e-6).  Gradients: backpropagation through ~35 BatchNorm + ReLU layers with random weights amplifies
+rounding noise by ~1e4 (torch's own FP32/cuDNN evaluation of the same trunk is 1e-3 .. 1e-2 away from float64,
+measured on B200; the repo's kernels are 0.5 .. 1x that, `scripts/head_grad_noise.py`), so each gradient's relative L2
+error is bounded by a multiple of the error that torch-FP32 shows on the same tensor (the reference's arithmetic),
+with an absolute floor.  The floor has to admit single ReLU sign flips: an activation within ~1e-6 sigma of zero
+(about one element per 5e5) lands on the other side in ANY fp32 evaluation, and one flipped element moves the
+gradients of a 32/64-channel stack by 3e-4 .. 1.5e-3 (diagnosed element by element with the script above).
+What the floor lets through is pinned separately and tightly: `test_trunk_backward_kernels_match_float64_of_own_operands`
+checks every kernel launch of a full backward pass against float64 arithmetic on that launch's own operands (flip
+free by construction, 2e-5), and the kernel-level tests below use well-conditioned inputs (1e-5)."""
 import copy
 
 import numpy as np
@@ -42,6 +47,17 @@ def _inputs(S, seed, H=96, W=176, C=128):
     occ1 = (torch.rand(S, 1, H, W, generator=g) < 0.35).float()
     occ2 = (torch.rand(S, 1, H, W, generator=g) < 0.35).float()
     return (x1 * occ1).cuda(), (x2 * occ2).cuda()
+
+
+def _check_split(split, x):
+    """split pair of x: both planes TF32-exact (low 13 mantissa bits clear, so the tensor core's operand truncation is
+    a no-op), hi = RN_tf32(x), lo = RN_tf32(x - hi): |x - hi| <= 2^-11 |x|, |x - hi - lo| <= 2^-22 |x|"""
+    hi, lo = split[0], split[1]
+    assert int((hi.contiguous().view(torch.int32) & 0x1fff).abs().max()) == 0
+    assert int((lo.contiguous().view(torch.int32) & 0x1fff).abs().max()) == 0
+    xd = x.double()
+    assert bool(((xd - hi.double()).abs() <= xd.abs() * 2.0 ** -11 + 1e-37).all())
+    assert bool(((xd - hi.double() - lo.double()).abs() <= xd.abs() * 2.0 ** -22 + 1e-37).all())
 
 
 def _rel(a, b):
@@ -141,7 +157,7 @@ def test_trunk_matches_float64(head, mode, S):
     h32, g32x1, g32x2 = _torch32_grads(head, state0, x1, x2, S, 1)
     gx1 = torch.cat([p[0].grad for p in ref_x])
     gx2 = torch.cat([p[1].grad for p in ref_x])
-    FACTOR, FLOOR = 8.0, 5e-5
+    FACTOR, FLOOR = 8.0, 3e-3
     assert _l2(a.grad, gx1) < max(FACTOR * _l2(g32x1, gx1), FLOOR), (_l2(a.grad, gx1), _l2(g32x1, gx1))
     assert _l2(b.grad, gx2) < max(FACTOR * _l2(g32x2, gx2), FLOOR), (_l2(b.grad, gx2), _l2(g32x2, gx2))
     p64, p32 = dict(h64.named_parameters()), dict(h32.named_parameters())
@@ -173,6 +189,10 @@ def test_trunk_graph_replay_matches_eager(head):
     (d0["translation_preds"][0].sum() + d0["rotation_preds"][0].sum() + d0["pyramid_motion"][0][0].sum()).backward()
     g_ref = {k: p.grad.clone() for k, p in head.named_parameters() if p.grad is not None}
     gx_ref = xs[0].grad.clone()
+    t_ref = d0["translation_preds"][0].detach().clone()
+    # drop the eager autograd graph: it keeps the parameters' AccumulateGrad nodes (created on the legacy default
+    # stream) alive, and the engine would then try to order that stream after the capturing one
+    del d0
     head.zero_grad()
     head.load_state_dict(st)
     head.use_cuda_graph = True
@@ -182,7 +202,7 @@ def test_trunk_graph_replay_matches_eager(head):
         head.zero_grad()
         d1 = head(ys)
         (d1["translation_preds"][0].sum() + d1["rotation_preds"][0].sum() + d1["pyramid_motion"][0][0].sum()).backward()
-    assert _rel(d1["translation_preds"][0], d0["translation_preds"][0]) < 1e-6
+    assert _rel(d1["translation_preds"][0], t_ref) < 1e-6
     assert _rel(ys[0].grad, gx_ref) < 1e-5
     for k, p in head.named_parameters():
         if k in g_ref and float(g_ref[k].abs().max()) > 0:
@@ -201,6 +221,85 @@ def test_weight_update_through_data_is_seen(head):
         o1 = head._trunk_own(x1, x2, 1)[0].clone()
         w.data.div_(1.5)
     assert float((o1 - o0).abs().max()) > 1e-6
+
+
+@pytest.mark.parametrize("mode", ["train", "frozen"])
+def test_trunk_backward_kernels_match_float64_of_own_operands(head, mode):
+    """Every data-gradient, weight-gradient and BatchNorm-backward launch of one full trunk backward pass (S = 2
+    samples, real layer shapes and magnitudes) against float64 arithmetic on the launch's OWN operands: independent of
+    what happened upstream (no ReLU-flip or amplification noise), so the bound is tight."""
+    import rslo_b200.layers.head_tc as HT
+    K = HT.K
+    head.train(True)
+    if mode == "frozen":
+        for m in head.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+    state0 = copy.deepcopy(head.state_dict())
+    x1, x2 = _inputs(2, 21)
+    worst = {"dgrad": 0.0, "wgrad": 0.0, "bn": 0.0}
+    counts = {"dgrad": 0, "wgrad": 0, "bn": 0}
+    l2 = lambda a, b: float((a.double() - b).norm() / b.norm().clamp_min(1e-300))
+    orig = (K.conv2d_tc_backward_weight, K.conv2d_tc_backward_data, K.bn_act_backward)
+
+    def spy_w(x_split, g_split, ksize, stride, **kw):
+        r = orig[0](x_split, g_split, ksize, stride, **kw)
+        x = (x_split[0].double() + x_split[1].double()).permute(0, 3, 1, 2)
+        g = (g_split[0].double() + g_split[1].double()).permute(0, 3, 1, 2)
+        cin, coutp = x.shape[1], g.shape[1]
+        ref = torch.nn.grad.conv2d_weight(x, (coutp, cin, ksize, ksize), g, stride=stride, padding=ksize // 2)
+        got = kw["scratch"].view(ksize * ksize, cin, coutp).permute(2, 1, 0).reshape(coutp, cin, ksize, ksize)
+        worst["wgrad"] = max(worst["wgrad"], l2(got, ref))
+        counts["wgrad"] += 1
+        return r
+
+    def spy_d(g_split, image_t, in_shape, ksize, stride, out=None, accumulate=False):
+        base = out.double().clone() if accumulate else None
+        r = orig[1](g_split, image_t, in_shape, ksize, stride, out=out, accumulate=accumulate)
+        B, H, W, cin = in_shape
+        coutp = g_split.shape[-1]
+        img = image_t.view(2, ksize * ksize, cin, coutp).double()
+        w = (img[0] + img[1]).permute(2, 1, 0).reshape(coutp, cin, ksize, ksize)
+        g = (g_split[0].double() + g_split[1].double()).permute(0, 3, 1, 2)
+        ref = torch.nn.grad.conv2d_input((B, cin, H, W), w, g, stride=stride, padding=ksize // 2).permute(0, 2, 3, 1)
+        got = r.double() - (base if base is not None else 0)
+        worst["dgrad"] = max(worst["dgrad"], l2(got, ref))
+        counts["dgrad"] += 1
+        return r
+
+    def spy_bn(dz, z, y, ipg, mean_rstd, gamma, relu, batch_stats, sums, g_split, dres, dres_acc, dgamma, dbeta, dbias):
+        orig[2](dz, z, y, ipg, mean_rstd, gamma, relu, batch_stats, sums, g_split, dres, dres_acc, dgamma, dbeta, dbias)
+        B, H, W, C = y.shape
+        d = dz.double() * ((z > 0).double() if relu else 1.0)
+        mr = mean_rstd.double()
+        mean = mr[:, :, 0].repeat_interleave(ipg, 0).view(B, 1, 1, C)
+        rstd = mr[:, :, 1].repeat_interleave(ipg, 0).view(B, 1, 1, C)
+        xhat = (y.double() - mean) * rstd
+        e = max(l2(dbeta, d.sum((0, 1, 2))), l2(dgamma, (d * xhat).sum((0, 1, 2))))
+        gam = gamma.double().view(1, 1, 1, C)
+        if batch_stats:
+            n = ipg * H * W
+            dg_ = d.view(B // ipg, n, C)
+            xh = xhat.view(B // ipg, n, C)
+            gy = (gam * rstd).view(B // ipg, ipg, 1, C)[:, :1].reshape(B // ipg, 1, C) * \
+                (dg_ - dg_.mean(1, keepdim=True) - xh * (dg_ * xh).mean(1, keepdim=True))
+            gy = gy.view(B, H, W, C)
+        else:
+            gy = gam * rstd * d
+        e = max(e, l2(g_split[0].double() + g_split[1].double(), gy))
+        worst["bn"] = max(worst["bn"], e)
+        counts["bn"] += 1
+
+    K.conv2d_tc_backward_weight, K.conv2d_tc_backward_data, K.bn_act_backward = spy_w, spy_d, spy_bn
+    try:
+        outs, _, _ = _own(head, x1, x2, 1)
+        _loss(outs, 2).backward()
+    finally:
+        K.conv2d_tc_backward_weight, K.conv2d_tc_backward_data, K.bn_act_backward = orig
+        head.zero_grad()
+        head.load_state_dict(state0)
+    assert counts["wgrad"] == 50 and counts["dgrad"] >= 49 and counts["bn"] == 45, counts
+    assert worst["wgrad"] < 2e-5 and worst["dgrad"] < 2e-5 and worst["bn"] < 2e-5, worst
 
 
 # ---- kernel-level tests of csrc/head_ops.cu through the C ABI (well-conditioned inputs, tight tolerance) --------
@@ -247,7 +346,7 @@ def test_bn_act_forward_backward_kernels(cuda, B, H, W, C, ipg, relu, res, train
     def rel(a, b):
         return float((a.double() - b.double()).abs().max() / b.double().abs().max())
     assert rel(z, zd.permute(0, 2, 3, 1)) < 1e-5
-    assert torch.equal(zsplit[0] + zsplit[1], z) and float((zsplit[1].abs() > zsplit[0].abs() * 2 ** -10 + 1e-30).sum()) == 0
+    _check_split(zsplit, z)
     if train:
         assert rel(rm_k, rm_ref) < 1e-6 and rel(rv_k, rv_ref) < 1e-6 and int(nbt) == G
     sums = torch.zeros(G, C, 2, dtype=torch.float64, device="cuda")
@@ -276,7 +375,7 @@ def test_pack_unpack_upcat_kernels(cuda):
     mask = torch.empty(B, H, W, device="cuda")
     K.head_pack_input(x1, x2, split, mask)
     cat = torch.cat([x1, x2], 1).permute(0, 2, 3, 1)
-    assert torch.equal(split[0] + split[1], cat)
+    _check_split(split, cat)
     assert torch.equal(mask, (x1.sum(1) != 0).float())
     dx = torch.randn(B, H, W, 2 * C, generator=g).cuda()
     g1, g2 = torch.empty_like(x1), torch.empty_like(x2)
@@ -288,7 +387,8 @@ def test_pack_unpack_upcat_kernels(cuda):
     dst = torch.zeros(2, B, 2 * H, 2 * W, ld, device="cuda")
     K.upcat_split(z, 2, ld, off, dst)
     up = torch.nn.functional.interpolate(z.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
-    assert torch.equal((dst[0] + dst[1])[..., off:off + 32], up) and float(dst[..., :off].abs().max()) == 0
+    _check_split(dst[..., off:off + 32], up)
+    assert float(dst[..., :off].abs().max()) == 0
     dcat = torch.randn(B, 2 * H, 2 * W, ld, generator=g).cuda()
     dz = torch.ones(B, H, W, 32, device="cuda")
     K.upcat_backward(dcat, (B, H, W, 32), 2, ld, off, dz, True)
