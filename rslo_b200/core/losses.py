@@ -90,7 +90,7 @@ class Aleat5_1ChamferL2NormalWeightedALLSVDLoss(Loss):
             focal_gamma = self.focal_gamma
         _alpha = self.alpha
         B = xyz_pred.shape[0]
-        loss = 0
+        loss = None
         res_R, res_T = [], []
         eye = torch.eye(3, device=xyz_pred.device, dtype=xyz_pred.dtype)
         for b in range(B):
@@ -100,8 +100,9 @@ class Aleat5_1ChamferL2NormalWeightedALLSVDLoss(Loss):
             thr = self._roi_threshold(dist)
             # Mahalanobis residual under the summed covariances + log-det regulariser, ROI mean:
             # one fused kernel forward, one backward (csrc/cov_residual.cu)
-            loss = loss + K.cov_residual(xyz_pred[b], xyz_target[b], cov_pred[b], cov_target[b], R_pred[b].detach(),
-                                         idx, dist, thr, self.reg_weight)
+            term = K.cov_residual(xyz_pred[b], xyz_target[b], cov_pred[b], cov_target[b], R_pred[b].detach(),
+                                  idx, dist, thr, self.reg_weight)
+            loss = term if loss is None else loss + term
 
             # ICP refinement on detached points (losses.py:440-488): the association gather, the
             # |cos(normal, q - p)|^2 weight and the ROI test all happen inside the Kabsch reduction
@@ -121,7 +122,12 @@ class Aleat5_1ChamferL2NormalWeightedALLSVDLoss(Loss):
             res_T.append(res_t_[None])
         res_R = torch.cat(res_R, dim=0)
         res_T = torch.cat(res_T, dim=0)
-        loss = loss / B
+        if B != 1:
+            loss = loss / B
+        if focal_gamma == 0 and loss.numel() == 1:
+            # x ** 0 == 1 and 1 / (1 + 1e-12) == 1 in fp32: the focal weight of a single term is exactly 1 and carries no
+            # gradient; what is left of `losses.py:492-497` is e^-alpha * loss + alpha (same rounding, 10 launches fewer)
+            return (torch.exp(-_alpha) * loss).reshape(()) + _alpha, res_R, res_T
         focal_weight = (torch.exp(-_alpha) * loss) ** focal_gamma
         focal_weight = focal_weight / (torch.sum(focal_weight) + 1e-12)
         loss = focal_weight * (torch.exp(-_alpha) * loss)

@@ -10,11 +10,18 @@
 //       (`:727-735`, kornia rotation_matrix_to_quaternion), target (t,q) maps (`rslo/data/dataset.py:52-116`),
 //       AdaptiveWeightedL2 on the pose and on the three pyramid levels (`rslo/core/losses.py:155-197`, focal_gamma 0).
 //
-// One CTA of 1024 threads per frame pair: every reduction (softmax max / sum, vote sums, loss sums) is a block
-// reduction in double precision in a fixed order -> deterministic; the maps are read once per pass.
+// Forward kernels: one thread-block CLUSTER of 8 x 1024 threads per frame pair; every reduction (softmax max / sum,
+// vote sums, loss sums) is a block reduction in double precision followed by an exchange of the CTA totals through
+// distributed shared memory, combined in rank order -> deterministic; cluster barriers separate the passes (and
+// order the global-memory maps one pass writes and the next pools).  Backward kernels: grid (chunks, B), the only
+// reduction they need (softmax backward's sum) is cheap and read-only, so every CTA of a pair repeats it.
 // Inputs from the trunk are NHWC with 32-channel rows (conv2d_tc.cu's narrow heads); outputs follow the reference's
 // NCHW contract.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace rslo {
 namespace {
@@ -96,6 +103,50 @@ __device__ __forceinline__ void block_max2(float& a, float& b, float* sh /* [2][
     __syncthreads();
 }
 
+// ---- thread-block cluster variants: the PT_CLUSTER CTAs of one image each reduce their share, exchange the
+// CTA totals through distributed shared memory and combine them in rank order (every CTA gets the same bits)
+constexpr int PT_CLUSTER = 8;
+
+template <int N>
+__device__ __forceinline__ void cluster_sum(double (&v)[N], double* sh /* [N][32] */, double* xch /* [2][N] */)
+{
+    cg::cluster_group cl = cg::this_cluster();
+    block_sum<N>(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) xch[i] = v[i];
+    }
+    cl.sync();
+    if (threadIdx.x < N) {
+        double t = 0.0;
+        for (unsigned r = 0; r < cl.num_blocks(); ++r) t += *cl.map_shared_rank(xch + threadIdx.x, r);
+        xch[N + threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = xch[N + i];
+    cl.sync();                                  // nobody overwrites xch while a neighbour still reads it
+}
+__device__ __forceinline__ void cluster_max2(float& a, float& b, float* sh /* [2][32] */, float* xch /* [4] */)
+{
+    cg::cluster_group cl = cg::this_cluster();
+    block_max2(a, b, sh);
+    if (threadIdx.x == 0) {
+        xch[0] = a;
+        xch[1] = b;
+    }
+    cl.sync();
+    if (threadIdx.x < 2) {
+        float t = -INFINITY;
+        for (unsigned r = 0; r < cl.num_blocks(); ++r) t = fmaxf(t, *cl.map_shared_rank(xch + threadIdx.x, r));
+        xch[2 + threadIdx.x] = t;
+    }
+    __syncthreads();
+    a = xch[2];
+    b = xch[3];
+    cl.sync();
+}
+
 // cell anchor of pixel (i, j) of a map that is `s` times coarser than the geometry's grid
 __device__ __forceinline__ V3 anchor(const rslo_tq_geom_t& G, int i, int j)
 {
@@ -127,7 +178,7 @@ __device__ __forceinline__ PixelTQ pixel_tq(const float* __restrict__ row, const
 // saved per pair: [0..1] max_t, max_r; [2..5] sum_t1, sum_t20, sum_r1, sum_r20; [6..8] A_t; [9] S_t; [10..13] A_q; [14] S_r
 constexpr int HT_SAVE = 16;
 
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __cluster_dims__(PT_CLUSTER, 1, 1) __launch_bounds__(PT_THREADS)
 k_head_tail_fwd(const float* __restrict__ tq32, const float* __restrict__ tl32, const float* __restrict__ rl32,
                 const float* __restrict__ mask, const float* __restrict__ py0_32, const float* __restrict__ py1_32,
                 rslo_tq_geom_t G, float* __restrict__ pose_t, float* __restrict__ pose_q, float* __restrict__ tq_g,
@@ -136,9 +187,14 @@ k_head_tail_fwd(const float* __restrict__ tq32, const float* __restrict__ tl32, 
                 float* __restrict__ pm0_pred, float* __restrict__ pm0_mask, float* __restrict__ base1,
                 float* __restrict__ base0, float* __restrict__ save)
 {
+    // grid (PT_CLUSTER, B): one cluster per image; CTA `crank` owns pixels crank*PT_THREADS + tid, + PT_CLUSTER*PT_THREADS, ...
     __shared__ double sh[9 * 32];
+    __shared__ double xch_d[2 * 9];
     __shared__ float shf[64];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ float xch_f[4];
+    cg::cluster_group cl = cg::this_cluster();
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int p_first = blockIdx.x * PT_THREADS + tid, p_step = PT_CLUSTER * PT_THREADS;
     const int H = G.H, W = G.W, HW = H * W;
     const float* m = mask + (size_t)b * HW;
     const float* tl = tl32 + (size_t)b * HW * 32;
@@ -147,16 +203,16 @@ k_head_tail_fwd(const float* __restrict__ tq32, const float* __restrict__ tl32, 
 
     // pass 1: maxima of the masked logits
     float mt = -INFINITY, mr = -INFINITY;
-    for (int p = tid; p < HW; p += PT_THREADS) {
+    for (int p = p_first; p < HW; p += p_step) {
         const bool on = __ldg(m + p) > 0.f;
         mt = fmaxf(mt, on ? __ldg(tl + (size_t)p * 32) : -1000.f);
         mr = fmaxf(mr, on ? __ldg(rl + (size_t)p * 32) : -1000.f);
     }
-    block_max2(mt, mr, shf);
+    cluster_max2(mt, mr, shf, xch_f);
     const float mt20 = mt / 20.f, mr20 = mr / 20.f;
     // pass 2: softmax denominators at temperature 1 and 20
     double s[4] = {0, 0, 0, 0};
-    for (int p = tid; p < HW; p += PT_THREADS) {
+    for (int p = p_first; p < HW; p += p_step) {
         const bool on = __ldg(m + p) > 0.f;
         const float xt = on ? __ldg(tl + (size_t)p * 32) : -1000.f;
         const float xr = on ? __ldg(rl + (size_t)p * 32) : -1000.f;
@@ -165,11 +221,11 @@ k_head_tail_fwd(const float* __restrict__ tq32, const float* __restrict__ tl32, 
         s[2] += (double)expf(xr - mr);
         s[3] += (double)expf(xr / 20.f - mr20);
     }
-    block_sum<4>(s, sh);
+    cluster_sum<4>(s, sh, xch_d);
     const float st1 = (float)s[0], st20 = (float)s[1], sr1 = (float)s[2], sr20 = (float)s[3];
     // pass 3: confidences, global (t,q), vote sums, finest pyramid level
     double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = tid; p < HW; p += PT_THREADS) {
+    for (int p = p_first; p < HW; p += p_step) {
         const int i = p / W, j = p - i * W;
         const float mk = __ldg(m + p);
         const bool on = mk > 0.f;
@@ -194,8 +250,8 @@ k_head_tail_fwd(const float* __restrict__ tq32, const float* __restrict__ tl32, 
         v[7] += (double)(q.qg[3] * cr);
         v[8] += (double)cr;
     }
-    block_sum<9>(v, sh);                        // also orders the pm2_mask stores before the pooling below
-    if (tid == 0) {
+    cluster_sum<9>(v, sh, xch_d);               // its cluster barriers also order the pm2_mask stores before the pooling
+    if (tid == 0 && blockIdx.x == 0) {
         const float St = (float)v[3], Sr = (float)v[8];
         float* sv = save + (size_t)b * HT_SAVE;
         sv[0] = mt; sv[1] = mr; sv[2] = st1; sv[3] = st20; sv[4] = sr1; sv[5] = sr20;
@@ -221,7 +277,7 @@ k_head_tail_fwd(const float* __restrict__ tq32, const float* __restrict__ tl32, 
         float* pmask = (lvl == 1 ? pm1_mask : pm0_mask) + (size_t)b * 2 * cn;
         float* ppred = (lvl == 1 ? pm1_pred : pm0_pred) + (size_t)b * 7 * cn;
         const float* praw = (lvl == 1 ? py1_32 : py0_32) + (size_t)b * cn * 32;
-        for (int p = tid; p < cn; p += PT_THREADS) {
+        for (int p = p_first; p < cn; p += p_step) {
             const int i = p / cw, j = p - i * cw;
             float mx = -INFINITY, a0 = 0.f, a1 = 0.f;
             for (int dy = -1; dy <= 1; ++dy) {
@@ -244,7 +300,7 @@ k_head_tail_fwd(const float* __restrict__ tq32, const float* __restrict__ tl32, 
             ppred[p] = r0.x * keep; ppred[cn + p] = r0.y * keep; ppred[2 * cn + p] = r0.z * keep; ppred[3 * cn + p] = r0.w * keep;
             ppred[4 * cn + p] = r1.x * keep; ppred[5 * cn + p] = r1.y * keep; ppred[6 * cn + p] = r1.z * keep;
         }
-        __syncthreads();
+        cl.sync();                              // level-1 masks of the whole image before level 0 pools them
         fine_mask = pmask;
         fine_occ = occ;
         fh = ch;
@@ -262,7 +318,7 @@ k_head_tail_bwd(const float* __restrict__ tq32, const float* __restrict__ mask, 
                 float* __restrict__ d_rl32, float* __restrict__ d_py1_32, float* __restrict__ d_py0_32)
 {
     __shared__ double sh[2 * 32];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int H = G.H, W = G.W, HW = H * W;
     const float* m = mask + (size_t)b * HW;
     const float* tq = tq32 + (size_t)b * HW * 32;
@@ -308,9 +364,12 @@ k_head_tail_bwd(const float* __restrict__ tq32, const float* __restrict__ mask, 
     }
     block_sum<2>(D, sh);
     const float Dt = (float)D[0], Dr = (float)D[1];
-    // pass 2: per-pixel gradients
+    // pass 2: per-pixel gradients.  The grid is (chunks, B): every CTA of an image repeats the cheap read-only
+    // pass 1 (same order -> the same D, bit for bit) and writes only its own share of the pixels, so the 6.5 MB of
+    // 32-channel gradient rows per image are written by ~70 SMs instead of one.
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = tid; p < HW; p += PT_THREADS) {
+    const int pstride = gridDim.x * PT_THREADS;
+    for (int p = blockIdx.x * PT_THREADS + tid; p < HW; p += pstride) {
         const int i = p / W, j = p - i * W;
         const float mk = __ldg(m + p);
         const bool on = mk > 0.f;
@@ -372,7 +431,7 @@ k_head_tail_bwd(const float* __restrict__ tq32, const float* __restrict__ mask, 
         const float* occ = (lvl == 1 ? base1 : base0) + (size_t)b * cn;
         const float* g = lvl == 1 ? g_pm1 : g_pm0;
         float* d = (lvl == 1 ? d_py1_32 : d_py0_32) + (size_t)b * cn * 32;
-        for (int p = tid; p < cn; p += PT_THREADS) {
+        for (int p = blockIdx.x * PT_THREADS + tid; p < cn; p += pstride) {
             const float keep = (g != nullptr && occ[p] > 0.f) ? 1.f : 0.f;
             float v[7];
 #pragma unroll
@@ -443,17 +502,21 @@ __device__ __forceinline__ void target_at(const rslo_tq_geom_t& G, int i, int j,
     tl = rotate_by_q(ts - p, qs_inv[0], V3{qs_inv[1], qs_inv[2], qs_inv[3]}) + p;
 }
 
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __cluster_dims__(PT_CLUSTER, 1, 1) __launch_bounds__(PT_THREADS)
 k_loss_tail_fwd(const float* __restrict__ T_pred, const float* __restrict__ q_pred, PyrLevel L0, PyrLevel L1, PyrLevel L2,
                 const float* __restrict__ res_r, const float* __restrict__ res_t, int identity_pose, rslo_tq_geom_t G, int B,
                 const float* __restrict__ alpha_t, const float* __restrict__ alpha_r, const float* __restrict__ alpha_pt,
                 const float* __restrict__ alpha_pr, float w_t, float w_r, float w_pt, float w_pr, float* __restrict__ tq_target,
                 float* __restrict__ save, float* __restrict__ losses /* [8] */, int* __restrict__ counter)
 {
+    // grid (PT_CLUSTER, B): one cluster per pair, the maps are shared out over its CTAs (see k_head_tail_fwd)
     __shared__ double sh[12 * 32];
+    __shared__ double xch_d[2 * 12];
     __shared__ float s_lab[8];
     __shared__ int s_last;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int p_first = blockIdx.x * PT_THREADS + tid, p_step = PT_CLUSTER * PT_THREADS;
+    if (tid == 0) s_last = 0;
     const int H = G.H, W = G.W, HW = H * W;
     if (tid == 0) {
         float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, T[3] = {0, 0, 0};
@@ -476,7 +539,7 @@ k_loss_tail_fwd(const float* __restrict__ T_pred, const float* __restrict__ q_pr
     const float qs[4] = {s_lab[3], s_lab[4], s_lab[5], s_lab[6]};
     const float qi[4] = {qs[0], -qs[1], -qs[2], -qs[3]};
     // target map at full resolution
-    for (int p = tid; p < HW; p += PT_THREADS) {
+    for (int p = p_first; p < HW; p += p_step) {
         const int i = p / W, j = p - i * W;
         V3 tl;
         target_at(G, i, j, ts, qi, tl);
@@ -492,7 +555,7 @@ k_loss_tail_fwd(const float* __restrict__ T_pred, const float* __restrict__ q_pr
         const int n = L.h * L.w;
         const float* pr = L.pred + (size_t)b * 7 * n;
         const float* mk = L.mask + (size_t)b * 2 * n;
-        for (int p = tid; p < n; p += PT_THREADS) {
+        for (int p = p_first; p < n; p += p_step) {
             const int i = p / L.w, j = p - i * L.w;
             V3 tl;
             target_at(G, i * L.stride, j * L.stride, ts, qi, tl);
@@ -510,8 +573,8 @@ k_loss_tail_fwd(const float* __restrict__ T_pred, const float* __restrict__ q_pr
             acc[l * 4 + 3] += (double)mr;
         }
     }
-    block_sum<12>(acc, sh);
-    if (tid == 0) {
+    cluster_sum<12>(acc, sh, xch_d);
+    if (tid == 0 && blockIdx.x == 0) {
         float* sv = save + (size_t)b * LT_SAVE;
         float lt = 0.f, lr = 0.f;
         for (int k = 0; k < 3; ++k) {
@@ -557,14 +620,14 @@ k_loss_tail_bwd(const float* __restrict__ T_pred, const float* __restrict__ q_pr
                 float w_pr, const float* __restrict__ save, const float* __restrict__ g_losses /* [8] */,
                 float* __restrict__ dT, float* __restrict__ dq, float* __restrict__ dalpha /* [4], zeroed */)
 {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;         // grid (chunks, B)
     const float* sv = save + (size_t)b * LT_SAVE;
     const float fw = 1.f / ((float)B + 1e-12f);
     const V3 ts = V3{sv[14], sv[15], sv[16]};
     const float qs[4] = {sv[17], sv[18], sv[19], sv[20]};
     const float qi[4] = {qs[0], -qs[1], -qs[2], -qs[3]};
     const float eat = expf(-*alpha_t), ear = expf(-*alpha_r), eapt = expf(-*alpha_pt), eapr = expf(-*alpha_pr);
-    if (tid == 0) {
+    if (tid == 0 && blockIdx.x == 0) {
         const float ct = g_losses[0] * w_t * fw * eat * 2.f / (3.f + 1e-12f);
         const float cr = g_losses[1] * w_r * fw * ear * 2.f / (4.f + 1e-12f);
         for (int k = 0; k < 3; ++k) dT[b * 3 + k] = ct * (T_pred[b * 3 + k] - sv[14 + k]);
@@ -595,7 +658,7 @@ k_loss_tail_bwd(const float* __restrict__ T_pred, const float* __restrict__ q_pr
         float* d = L.dpred + (size_t)b * 7 * n;
         const float ct = g_losses[2 + l] * w_pt * fw * eapt * 2.f / (3.f * sv[8 + l] + 1e-12f);
         const float cr = g_losses[5 + l] * w_pr * fw * eapr * 2.f / (4.f * sv[11 + l] + 1e-12f);
-        for (int p = tid; p < n; p += PT_THREADS) {
+        for (int p = blockIdx.x * PT_THREADS + tid; p < n; p += gridDim.x * PT_THREADS) {
             const int i = p / L.w, j = p - i * L.w;
             V3 tl;
             target_at(G, i * L.stride, j * L.stride, ts, qi, tl);
@@ -626,7 +689,7 @@ extern "C" int rslo_head_tail_forward(const float* tq32, const float* t_logit32,
         return (int)cudaErrorInvalidValue;
     }
     RSLO_COUNT();
-    k_head_tail_fwd<<<B, PT_THREADS, 0, (cudaStream_t)stream>>>(tq32, t_logit32, r_logit32, mask, py0_32, py1_32, geom, pose_t,
+    k_head_tail_fwd<<<dim3(PT_CLUSTER, B), PT_THREADS, 0, (cudaStream_t)stream>>>(tq32, t_logit32, r_logit32, mask, py0_32, py1_32, geom, pose_t,
                                                                pose_q, tq_map_g, t_conf, r_conf, pm2_pred, pm2_mask, pm1_pred,
                                                                pm1_mask, pm0_pred, pm0_mask, occ1, occ0, save);
     RSLO_CHECK_LAUNCH("rslo_head_tail_forward");
@@ -642,7 +705,10 @@ extern "C" int rslo_head_tail_backward(const float* tq32, const float* mask, con
 {
     if (B <= 0) return 0;
     RSLO_COUNT();
-    k_head_tail_bwd<<<B, PT_THREADS, 0, (cudaStream_t)stream>>>(tq32, mask, t_conf, r_conf, occ1, occ0, save, geom, g_pose_t,
+    int chunks = 148 / B;
+    if (chunks < 1) chunks = 1;
+    if (chunks > cdiv(geom.H * geom.W, PT_THREADS)) chunks = cdiv(geom.H * geom.W, PT_THREADS);
+    k_head_tail_bwd<<<dim3(chunks, B), PT_THREADS, 0, (cudaStream_t)stream>>>(tq32, mask, t_conf, r_conf, occ1, occ0, save, geom, g_pose_t,
                                                                g_pose_q, g_tq_map_g, g_t_conf, g_r_conf, g_pm2_pred, g_pm1_pred,
                                                                g_pm0_pred, d_tq32, d_t_logit32, d_r_logit32, d_py1_32, d_py0_32);
     RSLO_CHECK_LAUNCH("rslo_head_tail_backward");
@@ -665,7 +731,7 @@ extern "C" int rslo_loss_tail_forward(const float* T_pred, const float* q_pred, 
 {
     if (B <= 0) return 0;
     RSLO_COUNT();
-    k_loss_tail_fwd<<<B, PT_THREADS, 0, (cudaStream_t)stream>>>(
+    k_loss_tail_fwd<<<dim3(PT_CLUSTER, B), PT_THREADS, 0, (cudaStream_t)stream>>>(
         T_pred, q_pred, make_level(pm0_pred, pm0_mask, nullptr, geom.H, geom.W, 4),
         make_level(pm1_pred, pm1_mask, nullptr, geom.H, geom.W, 2), make_level(pm2_pred, pm2_mask, nullptr, geom.H, geom.W, 1),
         res_r, res_t, identity_pose, geom, B, alpha_t, alpha_r, alpha_pt, alpha_pr, w_t, w_r, w_pt, w_pr, tq_target, save,
@@ -684,7 +750,10 @@ extern "C" int rslo_loss_tail_backward(const float* T_pred, const float* q_pred,
     if (B <= 0) return 0;
     RSLO_CHECK(cudaMemsetAsync(dalpha4, 0, 4 * sizeof(float), (cudaStream_t)stream));
     RSLO_COUNT();
-    k_loss_tail_bwd<<<B, PT_THREADS, 0, (cudaStream_t)stream>>>(
+    int chunks = 148 / B;
+    if (chunks < 1) chunks = 1;
+    if (chunks > cdiv(geom.H * geom.W, PT_THREADS)) chunks = cdiv(geom.H * geom.W, PT_THREADS);
+    k_loss_tail_bwd<<<dim3(chunks, B), PT_THREADS, 0, (cudaStream_t)stream>>>(
         T_pred, q_pred, make_level(pm0_pred, pm0_mask, d_pm0, geom.H, geom.W, 4),
         make_level(pm1_pred, pm1_mask, d_pm1, geom.H, geom.W, 2), make_level(pm2_pred, pm2_mask, d_pm2, geom.H, geom.W, 1), geom,
         B, alpha_t, alpha_r, alpha_pt, alpha_pr, w_t, w_r, w_pt, w_pr, save, g_losses8, dT, dq, dalpha4);

@@ -377,6 +377,10 @@ class _HeadTrunkFn(torch.autograd.Function):
         run = engine.forward(x1.contiguous(), x2.contiguous(), ipg, record)
         ctx.engine, ctx.run = engine, run
         outs = tuple(run.outputs)
+        # the returned tensors get this node as grad_fn: keeping them on ctx.run would be a reference cycle that only
+        # the cycle collector frees, and a graph that lingers keeps the parameters' AccumulateGrad nodes (and the
+        # stream they were created on) alive into the next capture
+        run.outputs = None
         ctx.mark_non_differentiable(outs[-1])
         if not record:
             run.tape = None

@@ -107,13 +107,13 @@ class _LossTailFn(torch.autograd.Function):
         ctx.same_t, ctx.same_r = a_pt is a_t or a_pt.data_ptr() == a_t.data_ptr(), a_pr.data_ptr() == a_r.data_ptr()
         ctx.save_for_backward(*ts[:8], a_t, a_r, a_pt, a_pr, save)
         ctx.mark_non_differentiable(tq_target)
-        return (*[losses[i:i + 1] for i in range(8)], tq_target)
+        return losses, tq_target
 
     @staticmethod
-    def backward(ctx, *gs):
+    def backward(ctx, g8, _g_target):
         T_pred, q_pred, pm0p, pm0m, pm1p, pm1m, pm2p, pm2m, a_t, a_r, a_pt, a_pr, save = ctx.saved_tensors
         dev = T_pred.device
-        g = torch.stack([torch.zeros((), device=dev) if v is None else v.reshape(()) for v in gs[:8]]).contiguous()
+        g = g8.contiguous()
         dT, dq = torch.empty_like(T_pred), torch.empty_like(q_pred)
         d0, d1, d2 = torch.empty_like(pm0p), torch.empty_like(pm1p), torch.empty_like(pm2p)
         da = torch.empty(4, dtype=torch.float32, device=dev)
@@ -129,8 +129,8 @@ class _LossTailFn(torch.autograd.Function):
 def loss_tail(T_pred, q_pred, pyramid, res_r, res_t, alphas, weights, identity_pose, geom):
     """pyramid = [[pred0, mask0], [pred1, mask1], [pred2, mask2]] (coarse to fine); alphas / weights in the order
     (translation, rotation, pyramid translation, pyramid rotation).
-    -> (T_loss, R_loss, [pyT_0..2], [pyR_0..2], tq_map_target)"""
+    -> (losses8 = [T, R, pyT_0..2, pyR_0..2] as ONE tensor, tq_map_target): a caller that combines the eight terms with
+    one weighted sum keeps the backward pass at one kernel (eight separate outputs cost a zeros + stack per step)"""
     (p0, m0), (p1, m1), (p2, m2) = pyramid
-    o = _LossTailFn.apply(T_pred, q_pred, p0, m0, p1, m1, p2, m2, res_r.detach(), res_t.detach(), *alphas, tuple(weights),
-                          bool(identity_pose), geom)
-    return o[0], o[1], list(o[2:5]), list(o[5:8]), o[8]
+    return _LossTailFn.apply(T_pred, q_pred, p0, m0, p1, m1, p2, m2, res_r.detach(), res_t.detach(), *alphas,
+                             tuple(weights), bool(identity_pose), geom)

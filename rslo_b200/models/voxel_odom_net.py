@@ -73,6 +73,23 @@ def _record_stream_tree(obj, stream, _seen=None):
         _record_stream_tree(vars(obj), stream, _seen)
 
 
+class _LazyOutputs(dict):
+    """Output dict whose display-only entries are computed when somebody reads them (`ret["feature_mask"]`)."""
+    lazy = {}
+
+    def __missing__(self, key):
+        fn = self.lazy.get(key)
+        if fn is None:
+            raise KeyError(key)
+        val = self[key] = fn()
+        return val
+
+    def get(self, key, default=None):
+        if key in self or key in self.lazy:
+            return self[key]
+        return default
+
+
 def _detach_tree(x, to_cpu=False):
     if isinstance(x, torch.Tensor):
         x = x.detach()
@@ -302,12 +319,24 @@ class UnVoxelOdomNetICP3(nn.Module):
             head_in[0].register_hook(lambda g, _cb=cb: (_cb(), g)[1])
         preds_dict = self.odom_predictor(head_in, tq_map_gt=None)
         if self.training or self.testing:
-            with torch.no_grad():
-                preds_dict["feature_mask"] = torch.cat(
-                    [(torch.sum(torch.cat(spatial_features[s * T:(s + 1) * T], dim=1), dim=1, keepdim=True) != 0).float()
-                     for s in range(S)], dim=0)
-                disp = [torch.mean(sf.detach(), dim=1, keepdim=True) for sf in spatial_features]
-                preds_dict["middle_feature"] = [(d - torch.min(d)) / (torch.max(d) - torch.min(d) + 1e-12) for d in disp]
+            # display maps of the training log (`voxel_odom_net.py:449-462`, consumed every display_step at
+            # `train_hdf5.py:750`): ~40 small launches over the BEV maps.  With the reference's host_outputs they are
+            # produced every step as there; with host_outputs=False they are produced on first access.
+            def feature_mask(sf=spatial_features):
+                with torch.no_grad():
+                    return torch.cat(
+                        [(torch.sum(torch.cat(sf[s * T:(s + 1) * T], dim=1), dim=1, keepdim=True) != 0).float()
+                         for s in range(S)], dim=0)
+
+            def middle_feature(sf=spatial_features):
+                with torch.no_grad():
+                    disp = [torch.mean(f.detach(), dim=1, keepdim=True) for f in sf]
+                    return [(d - torch.min(d)) / (torch.max(d) - torch.min(d) + 1e-12) for d in disp]
+            if example.get("host_outputs", True) or not self.training:
+                preds_dict["feature_mask"] = feature_mask()
+                preds_dict["middle_feature"] = middle_feature()
+            else:
+                preds_dict["_lazy_display"] = {"feature_mask": feature_mask, "middle_feature": middle_feature}
         preds_dict["middle_conf_preds"] = middle_conf_preds
         preds_dict["voxel_features"] = voxel_features
         preds_dict["voxel_coords"] = coors
@@ -353,8 +382,11 @@ class UnVoxelOdomNetICP3(nn.Module):
         preds_dict = self.network_forward(voxels, num_points, coors, batch_size_dev, example=example)
         if self.training:
             ret = self.loss(example, preds_dict)
+            lazy = preds_dict.get("_lazy_display")
+            if lazy is not None:
+                ret = _LazyOutputs(ret)
+                ret.lazy = lazy
             ret2 = {
-                "middle_feature": preds_dict["middle_feature"], "feature_mask": preds_dict["feature_mask"],
                 "t_conf": preds_dict["t_conf"], "r_conf": preds_dict["r_conf"],
                 "pyramid_motion": preds_dict["pyramid_motion"], "dynamic_sigma": -1, "transformed_inputs": None,
                 "tq_map_g": preds_dict["tq_map_g"], "local_motion": None, "down_masks": None,
@@ -362,6 +394,8 @@ class UnVoxelOdomNetICP3(nn.Module):
             }
             # the reference copies these ~10 maps to the host every step (voxel_odom_net.py:535-538);
             # `host_outputs=False` in the example keeps them on the device (detached)
+            if lazy is None:
+                ret2["middle_feature"], ret2["feature_mask"] = preds_dict["middle_feature"], preds_dict["feature_mask"]
             ret.update(_detach_tree(ret2, to_cpu=example.get("host_outputs", True)))
             return ret
         t_pred, r_pred = preds_dict["translation_preds"], preds_dict["rotation_preds"]
@@ -392,9 +426,20 @@ class UnVoxelOdomNetICP3(nn.Module):
             pyramid_rotation_loss=self._pyramid_rotation_loss,
             pyramid_translation_loss=self._pyramid_translation_loss, consistency_loss=self._consistency_loss)
         pyramid_num = len(pyramid_T_losses)
-        for i, (t_loss, r_loss) in enumerate(zip(pyramid_T_losses, pyramid_R_losses)):
-            pyramid_loss = pyramid_loss + self._pyloss_exp_w_base ** (pyramid_num - i) * (t_loss + r_loss)
-        loss = translation_loss + rotation_loss + pyramid_loss + C_loss
+        l8 = self.__dict__.pop("_losses8", None)
+        if l8 is not None and pyramid_num == 3:
+            # fused loss tail: loss = T + R + sum_i base^(n-i) (pyT_i + pyR_i) + C as one weighted sum of its [8] output
+            w8 = self.__dict__.get("_loss_w8")
+            if w8 is None or w8.device != l8.device:
+                pw = [self._pyloss_exp_w_base ** (pyramid_num - i) for i in range(pyramid_num)]
+                w8 = self.__dict__["_loss_w8"] = torch.tensor([1.0, 1.0] + pw + pw, dtype=l8.dtype, device=l8.device)
+            loss = (l8 * w8).sum().reshape(1) + C_loss
+            with torch.no_grad():
+                pyramid_loss = (l8[2:] * w8[2:]).sum().reshape(1)
+        else:
+            for i, (t_loss, r_loss) in enumerate(zip(pyramid_T_losses, pyramid_R_losses)):
+                pyramid_loss = pyramid_loss + self._pyloss_exp_w_base ** (pyramid_num - i) * (t_loss + r_loss)
+            loss = translation_loss + rotation_loss + pyramid_loss + C_loss
         self.end_timer("Create_loss forward")
         return {"loss": loss, "translation_loss": translation_loss.detach(), "rotation_loss": rotation_loss.detach(),
                 "pyramid_loss": pyramid_loss.detach(), "C_loss": C_loss.detach(),
@@ -471,7 +516,7 @@ class UnVoxelOdomNetICP3(nn.Module):
                         transformed_p1, transformed_p1_gt, cov_pred=point_confs[0], cov_target=point_confs[1],
                         R_pred=R_pred, t_pred=T_pred, normal_pred=transformed_normal1.detach(),
                         normal_target=transformed_normal1_gt.detach(), mask=None, icp_iter=icp_iter)
-                    C_loss = C_loss + (1 - warm_weight) * weight * l / S
+                    C_loss = C_loss + l * ((1 - warm_weight) * weight / S)
                 res_rs.append(res_r)
                 res_ts.append(res_t)
             res_r, res_t = (res_rs[0], res_ts[0]) if S == 1 else (torch.cat(res_rs), torch.cat(res_ts))
@@ -581,7 +626,7 @@ class UnVoxelOdomNetICP3(nn.Module):
         geom = self.__dict__.get("_loss_geom")
         if geom is None or (geom.H, geom.W) != (H, W):
             geom = self.__dict__["_loss_geom"] = loss_geometry(H, W, self.odom_predictor.point_cloud_range)
-        T_loss, R_loss, pyT, pyR, tq_map = loss_tail(T_pred, q_pred, pyramid_preds, res_r, res_t,
-                                                     [m.alpha for m in mods], [m._loss_weight for m in mods],
-                                                     identity_pose, geom)
-        return (T_loss, R_loss, *pyT, *pyR, tq_map)
+        l8, tq_map = loss_tail(T_pred, q_pred, pyramid_preds, res_r, res_t, [m.alpha for m in mods],
+                               [m._loss_weight for m in mods], identity_pose, geom)
+        self.__dict__["_losses8"] = l8          # picked up by loss(): one weighted sum instead of eight scalar chains
+        return (*[l8[i:i + 1] for i in range(8)], tq_map)

@@ -49,8 +49,10 @@ torch.cuda.synchronize()
 t0 = time.time()
 for _ in range(args.steps):
     step()
+t_host = time.time() - t0
 torch.cuda.synchronize()
-print(f"wall ms/step {1e3 * (time.time() - t0) / args.steps:.2f}  ({args.pairs} pairs)")
+print(f"wall ms/step {1e3 * (time.time() - t0) / args.steps:.2f}  ({args.pairs} pairs); host time to ENQUEUE a step "
+      f"{1e3 * t_host / args.steps:.2f} ms (if ~= wall, the step is launch-bound)")
 
 # stage walls (each stage synchronised): forward pieces of ONE pair
 a, b = pairs[0]

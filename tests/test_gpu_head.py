@@ -205,7 +205,7 @@ def test_trunk_graph_replay_matches_eager(head):
     assert _rel(d1["translation_preds"][0], t_ref) < 1e-6
     assert _rel(ys[0].grad, gx_ref) < 1e-5
     for k, p in head.named_parameters():
-        if k in g_ref and float(g_ref[k].abs().max()) > 0:
+        if k in g_ref and float(g_ref[k].abs().max()) > 1e-7:       # (softmax-logit biases: true gradient 0, noise only)
             assert _rel(p.grad, g_ref[k]) < 1e-4, k
     head.zero_grad()
 

@@ -243,3 +243,25 @@ def test_stress_grid_end_to_end_matches_oracle(cuda):
                                    atol=1e-5, err_msg=k)
     ret["loss"].sum().backward()
     assert torch.isfinite(net.odom_predictor.blocks[0][0].conv1.conv1.weight.grad).all()
+
+
+def test_display_outputs_on_demand_equal_the_eager_ones(net):
+    """`feature_mask` / `middle_feature` (display maps of the training log, `voxel_odom_net.py:449-462`) are produced
+    eagerly with the reference's host_outputs and on first access with host_outputs=False: same values, same keys."""
+    net, vg = net
+    onet.fill_weights(net, 11)
+    net.global_step.fill_(2000)
+    net._step_host = None
+    net.train()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    pts = [torch.from_numpy(f).cuda() for f in mg.make_frames(5, 16, 600, 2)]
+    a = net({"points": pts})                                    # host_outputs defaults to the reference's behaviour
+    net.load_state_dict(sd0)
+    b = net({"points": pts, "host_outputs": False})
+    assert "feature_mask" in a and not dict.__contains__(b, "feature_mask")
+    assert torch.equal(a["feature_mask"], b["feature_mask"].cpu())
+    assert dict.__contains__(b, "feature_mask") and b.get("middle_feature") is not None
+    for x, y in zip(a["middle_feature"], b["middle_feature"]):
+        assert torch.equal(x, y.cpu())
+    assert torch.equal(a["loss"].detach().cpu(), b["loss"].detach().cpu())
+    net.zero_grad()
