@@ -335,6 +335,23 @@ int rslo_cov_residual_backward(const float* pred, const float* target, const int
                                const float* grad_loss, float* grad_pred, float* grad_target, float* grad_cov_pred,
                                float* grad_cov_target, rslo_stream_t stream);
 
+/* ---- a6 (covariance decoder): BatchNorm1d + LeakyReLU over stacked frames (csrc/bn1d_seg.cu) ---------------
+ * Replaces nn.BatchNorm1d(C) + nn.LeakyReLU on `.features` after the decoder's convolutions
+ * (rslo/models/middle.py:181-213).  x, z [N, C] rows of G stacked frames, frame g = seg_rows_host[g] consecutive rows
+ * (G <= 16, C a multiple of 4).  training != 0: every frame is normalised with its own batch statistics (biased
+ * variance) and running_mean / running_var (may be NULL) move once per non-empty frame, in frame order (momentum,
+ * unbiased variance), num_batches_tracked += frames; stats: double [G][C][2] scratch ZEROED by the caller.
+ * training == 0: running statistics.  slope >= 0: LeakyReLU(slope) follows; slope < 0: no activation.
+ * mean_rstd: float [G][C][2] saved for the backward.
+ * Backward: dz, x -> dx, dgamma [C], dbeta [C] (summed over the frames); sums: double [G][C][2], ZEROED by the caller. */
+int rslo_bn1d_seg_forward(const float* x, int C, const int* seg_rows_host, int G, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, long long* num_batches_tracked, float eps,
+                          float momentum, int training, float slope, double* stats, float* z, float* mean_rstd,
+                          rslo_stream_t stream);
+int rslo_bn1d_seg_backward(const float* dz, const float* x, int C, const int* seg_rows_host, int G, const float* mean_rstd,
+                           const float* gamma, const float* beta, float slope, int batch_stats, double* sums, float* dx,
+                           float* dgamma, float* dbeta, rslo_stream_t stream);
+
 /* ---- f-N2: the optimizer step in two launches (csrc/optim.cu) --------------------------------------------
  * Replaces torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0) (train_hdf5.py:671) followed by
  * OptimWrapper.step() (rslo/torchplus/train/fastai_optim.py:181-194: p *= 1 - wd*lr on every trainable parameter,

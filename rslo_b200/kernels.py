@@ -697,3 +697,48 @@ def adam_step(table, n_chunks, flat, exp_avg, exp_avg_sq, sumsq, grad_scale, max
                              float(weight_decay), 1 if true_wd else 0, int(step), 1 if write_clipped_grad else 0,
                              stream()), "rslo_adam_step")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# covariance decoder: BatchNorm1d + LeakyReLU over stacked frames (csrc/bn1d_seg.cu)
+# ------------------------------------------------------------------------------------------------
+def _seg_array(seg):
+    arr = (C.c_int * len(seg))(*[int(v) for v in seg])
+    return arr
+
+
+def _cost_bn1d(res_, x, *a, **k):
+    return 12 * x.numel(), 0
+
+
+@_profiled("bn1d_seg", _cost_bn1d)
+def bn1d_seg_forward(x, seg, gamma, beta, running_mean, running_var, nbt, eps, momentum, training, slope):
+    """x [N,C] rows of len(seg) stacked frames -> (z, mean_rstd [G,C,2]); see include/rslo_b200.h"""
+    x = _f32(x)
+    n, c = x.shape
+    assert sum(int(v) for v in seg) == n
+    G = len(seg)
+    z = torch.empty_like(x)
+    mean_rstd = torch.empty((G, c, 2), dtype=torch.float32, device=x.device)
+    stats = torch.zeros((G, c, 2), dtype=torch.float64, device=x.device) if training else None
+    check(lib.rslo_bn1d_seg_forward(ptr(x), c, _seg_array(seg), G, ptr(gamma), ptr(beta), ptr(running_mean),
+                                    ptr(running_var), ptr(nbt), float(eps), float(momentum), 1 if training else 0,
+                                    float(slope), ptr(stats), ptr(z), ptr(mean_rstd), stream()), "rslo_bn1d_seg_forward")
+    _count(2 if training else 1)
+    return z, mean_rstd
+
+
+@_profiled("bn1d_seg", _cost_bn1d)
+def bn1d_seg_backward(dz, x, seg, mean_rstd, gamma, beta, slope, batch_stats):
+    """-> (dx [N,C], dgamma [C], dbeta [C])"""
+    dz, x = _f32(dz), _f32(x)
+    n, c = x.shape
+    G = len(seg)
+    dx = torch.empty_like(x)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    sums = torch.zeros((G, c, 2), dtype=torch.float64, device=x.device)
+    check(lib.rslo_bn1d_seg_backward(ptr(dz), ptr(x), c, _seg_array(seg), G, ptr(mean_rstd), ptr(gamma), ptr(beta),
+                                     float(slope), 1 if batch_stats else 0, ptr(sums), ptr(dx), ptr(dgb[0]), ptr(dgb[1]),
+                                     stream()), "rslo_bn1d_seg_backward")
+    _count(2)
+    return dx, dgb[0], dgb[1]

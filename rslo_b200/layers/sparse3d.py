@@ -11,6 +11,7 @@ import os
 
 import torch
 from torch import nn
+from torch.nn import functional as F
 
 from .. import kernels as K
 
@@ -84,6 +85,7 @@ class SparseConvTensor:
 # FP32-level accuracy); the narrow layers (7/16 channels) stay on the FP32 FFMA kernel.
 # RSLO_SPCONV_TC=0 forces the FFMA kernel everywhere.
 USE_TC = os.environ.get("RSLO_SPCONV_TC", "1") != "0"
+USE_OWN_BN1D = os.environ.get("RSLO_OWN_BN1D", "1") != "0"     # A/B switch: 0 = torch native_batch_norm per frame
 
 
 class _DenseFn(torch.autograd.Function):
@@ -200,6 +202,28 @@ class _SpConvFn(torch.autograd.Function):
         return gi, gw, gb_fused, None, None, None, None, None
 
 
+class _SegBNActFn(torch.autograd.Function):
+    """BatchNorm1d (+ LeakyReLU) over the rows of stacked frames with per-frame batch statistics (csrc/bn1d_seg.cu);
+    updates the module's running statistics frame after frame like the reference's per-frame encoder calls."""
+
+    @staticmethod
+    def forward(ctx, feat, gamma, beta, mod, seg, slope):
+        feat = feat.contiguous()
+        training = mod.training
+        z, mean_rstd = K.bn1d_seg_forward(feat, seg, gamma, beta, mod.running_mean, mod.running_var,
+                                          mod.num_batches_tracked, mod.eps, mod.momentum, training, slope)
+        ctx.seg, ctx.slope, ctx.training = seg, slope, training
+        ctx.save_for_backward(feat, gamma, beta, mean_rstd)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        feat, gamma, beta, mean_rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = K.bn1d_seg_backward(dz.contiguous(), feat, ctx.seg, mean_rstd, gamma, beta, ctx.slope,
+                                                ctx.training)
+        return dx, dgamma, dbeta, None, None, None
+
+
 def _triple(v):
     return tuple(v) if isinstance(v, (list, tuple)) else (v, v, v)
 
@@ -296,6 +320,16 @@ class SparseSequential(nn.Sequential):
         plan, i = [], 0
         while i < len(mods):
             m = mods[i]
+            if (isinstance(m, nn.BatchNorm1d) and m.affine and m.track_running_stats and m.momentum is not None
+                    and m.num_features % 4 == 0 and USE_OWN_BN1D):
+                # BatchNorm1d (+ LeakyReLU) over the stacked frames: csrc/bn1d_seg.cu, per-frame statistics
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU):
+                    plan.append((m, "bn", mods[i + 1].negative_slope))
+                    i += 2
+                else:
+                    plan.append((m, "bn", -1.0))
+                    i += 1
+                continue
             if isinstance(m, SparseConvolution):
                 j = i + 1
                 while j < len(mods) and type(mods[j]).__name__ == "Empty":
@@ -314,7 +348,17 @@ class SparseSequential(nn.Sequential):
         if self._plan is None:
             self._plan = self._build_plan()
         for m, act, slope in self._plan:
-            if isinstance(m, SparseConvolution):
+            if act == "bn":
+                if isinstance(x, SparseConvTensor) and x.features.is_cuda:
+                    if x.n > 0:
+                        seg = tuple(x.seg) if x.seg is not None else (x.features.shape[0],)
+                        x = x.shadow(_SegBNActFn.apply(x.features, m.weight, m.bias, m, seg, slope))
+                else:                               # dense / CPU input: the torch modules
+                    f = x.features if isinstance(x, SparseConvTensor) else x
+                    f = m(f)
+                    f = F.leaky_relu(f, slope) if slope >= 0 else f
+                    x = x.shadow(f) if isinstance(x, SparseConvTensor) else f
+            elif isinstance(m, SparseConvolution):
                 m.fused_act, m.fused_slope = act, slope
                 x = m(x)
             elif isinstance(x, SparseConvTensor):

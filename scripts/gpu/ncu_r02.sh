@@ -1,0 +1,18 @@
+#!/bin/bash
+# ncu evidence for round 2: $1 = tag (default r02).  (1) launch list of one timed step (2 pairs per GPU, the bench's
+# workload), (2) --set full captures of the dominant kernels inside the same bench command.
+TAG=${1:-r02}
+mkdir -p gpurun_out
+B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-extras"
+RSLO_BENCH_CUDA_PROFILER=1 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/ncu_bench_$TAG.log 2>&1
+wc -l gpurun_out/launches_$TAG.csv
+full() {  # name regex count
+  RSLO_BENCH_CUDA_PROFILER=1 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$2" -c $3 -f -o gpurun_out/prof_${TAG}_$1 $B > gpurun_out/ncu_$1.log 2>&1
+  tail -1 gpurun_out/ncu_$1.log | cut -c1-200
+}
+full conv2d_tc '^k_conv2d_tc$' 24
+full spconv_tc '^k_spconv_tc$' 10
+full spconv_tc_wgrad 'k_spconv_tc_wgrad' 4
+full conv2d_wgrad_tc 'k_conv2d_wgrad_tc' 8
+full spconv_fwd '^k_spconv_fwd$' 3
+ls -la gpurun_out/*.ncu-rep

@@ -440,3 +440,55 @@ def test_conv2d_tensor_core_matches_fp64(cuda, cin, cout, h, w, ks, st, B):
     assert rel(acc - base, xd.grad.permute(0, 2, 3, 1)) < 5e-6
     dw = K.conv2d_tc_backward_weight(xs, gs, ks, st, cout_real=cout)
     assert dw.shape == wt.shape and rel(dw, wd.grad) < 5e-6
+
+
+@pytest.mark.parametrize("C,seg,train,slope", [(16, (1000, 2500, 37, 4000), True, 0.01), (32, (777, 1), True, 0.01),
+                                               (16, (5000,), True, -1.0), (32, (300, 0, 900), False, 0.01),
+                                               (64, (40000, 39000, 25000, 26000), True, 0.01)])
+def test_bn1d_over_stacked_frames_matches_float64(cuda, C, seg, train, slope):
+    """csrc/bn1d_seg.cu: BatchNorm1d (+ LeakyReLU) with per-frame statistics over stacked frames against float64
+    torch.nn.functional.batch_norm applied frame by frame (`rslo/models/middle.py:181-213` run once per frame):
+    outputs, running statistics (updated frame after frame), num_batches_tracked, dx, dgamma, dbeta."""
+    from rslo_b200 import kernels as K
+    g = torch.Generator().manual_seed(C + len(seg))
+    n = sum(seg)
+    x = (torch.randn(n, C, generator=g) * 1.7 + 0.4).cuda()
+    gamma = (0.5 + torch.rand(C, generator=g)).cuda()
+    beta = (0.3 * torch.randn(C, generator=g)).cuda()
+    rm = (0.1 * torch.randn(C, generator=g)).cuda()
+    rv = (0.5 + torch.rand(C, generator=g)).cuda()
+    dz = torch.randn(n, C, generator=g).cuda()
+    eps, mom = 1e-5, 0.1
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    outs, frames = [], 0
+    for f in torch.split(xd, list(seg)):
+        if f.shape[0] == 0:
+            continue
+        if train and f.shape[0] == 1:           # torch refuses one value per channel; the statistics are still defined
+            mu = f[0]
+            o = (f - mu) * torch.rsqrt(torch.zeros_like(mu) + eps) * gd + bd
+            rm_ref = (1 - mom) * rm_ref + mom * mu.detach()
+            rv_ref = (1 - mom) * rv_ref
+        else:
+            o = torch.nn.functional.batch_norm(f, rm_ref, rv_ref, gd, bd, training=train, momentum=mom, eps=eps)
+        frames += 1
+        outs.append(torch.nn.functional.leaky_relu(o, slope) if slope >= 0 else o)
+    zd = torch.cat(outs)
+    zd.backward(dz.double())
+
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    rm_k, rv_k = rm.clone(), rv.clone()
+    z, mr = K.bn1d_seg_forward(x, seg, gamma, beta, rm_k, rv_k, nbt, eps, mom, train, slope)
+    dx, dgamma, dbeta = K.bn1d_seg_backward(dz, x, seg, mr, gamma, beta, slope, train)
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    assert rel(z, zd) < 1e-5
+    if train:
+        assert rel(rm_k, rm_ref) < 1e-6 and rel(rv_k, rv_ref) < 1e-5 and int(nbt) == frames
+    else:
+        assert torch.equal(rm_k, rm) and torch.equal(rv_k, rv) and int(nbt) == 0
+    assert rel(dx, xd.grad) < 2e-5
+    assert rel(dgamma, gd.grad) < 1e-5 and rel(dbeta, bd.grad) < 1e-5
