@@ -317,6 +317,11 @@ class Runner:
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
         self.h2d_bytes = self.d2h_bytes = 0
         self.prefetch = {}
+        self.prefetcher = None
+        if os.environ.get("RSLO_BENCH_PREFETCH_THREAD", "0") != "0":     # measured: GIL contention outweighs the overlap
+            from rslo_b200.data.prefetch import PreparedPrefetcher
+            self.prefetcher = PreparedPrefetcher(net, dev)
+        self.host_s = 0.0
 
     def prepared_step(self, i, from_host):
         """net.prepare(): voxelisation + index tables of ALL samples of step i on a side stream (the reference does
@@ -328,7 +333,10 @@ class Runner:
             pts += [a, b]
             if from_host:
                 self.h2d_bytes += a.numel() * 4 + b.numel() * 4
-        return self.net.prepare({"points": pts, "n_samples": self.ppg, "host_outputs": False})
+        ex = {"points": pts, "n_samples": self.ppg, "host_outputs": False}
+        if self.prefetcher is not None:
+            return self.prefetcher.submit(ex)            # worker thread (rslo_b200/data/prefetch.py)
+        return self.net.prepare(ex)
 
     def step(self, i, from_host):
         """one step = the ppg samples of the batch through ONE net(example) call (example["n_samples"] = ppg):
@@ -339,6 +347,8 @@ class Runner:
         ex = self.prefetch.pop((i, from_host), None)
         if ex is None:
             ex = self.prepared_step(i, from_host)
+        if hasattr(ex, "result"):
+            ex = ex.result()
         if self.train:
             ret = net(ex)
             ret["loss"].sum().backward()
@@ -370,10 +380,12 @@ class Runner:
         torch.cuda.synchronize()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]
         evs[0].record()
+        t_host = time.time()
         for i in range(nsteps):
             self.flush.zero_()                                             # L2 flush between steps
             self.step(first + i, from_host)
             evs[i + 1].record()
+        self.host_s = time.time() - t_host                                 # time the training thread needed to ENQUEUE
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
@@ -385,11 +397,18 @@ class Runner:
             ms = float(t.item())
         return ms, per
 
+    def close(self):
+        self.prefetch.clear()
+        if self.prefetcher is not None:
+            self.prefetcher.shutdown()
+            self.prefetcher = None
+
     def quick(self, steps, warmup):
         """pairs/s of this workload, device-resident inputs (used for the extras)"""
         for i in range(warmup):
             self.step(i, False)
         ms, per = self.timed(steps, False, warmup)
+        self.close()
         per.sort()
         return {"value": self.world * self.ppg * steps / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms / steps,
                 "ms_per_step_median": per[len(per) // 2], "steps": steps, "warmup": warmup}
@@ -559,6 +578,7 @@ def main():
         torch.cuda.profiler.stop()
     launches = K.kernel_launch_count() - l0
     run_train = run.train
+    host_ms = 1e3 * run.host_s / args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = world * ppg * args.steps / (ms / 1e3)
 
@@ -603,6 +623,7 @@ def main():
     extra = None
     if rank == 0 and world == 1 and not args.no_extras and args.workload == "train":
         extra = {}
+        run.close()
         del run
         torch.cuda.empty_cache()
         try:
@@ -617,7 +638,7 @@ def main():
                 r = Runner(c, dev, rank, world)
                 sweep[str(nv)] = r.quick(8, 4)
                 prep = r.net.prepare({"points": list(r.resident[0])})
-                sweep[str(nv)]["voxels_per_frame"] = [int(v.shape[0]) for v in prep["_prepared"]["frames"]["features"]]
+                sweep[str(nv)]["voxels_per_frame"] = [int(v.shape[0]) for v in prep["_prepared"]["finish"]()["features"]]
                 del r, prep
                 torch.cuda.empty_cache()
             extra["stress"] = {"config": public_config(workload_config("stress")), "max_voxels_sweep": sweep}
@@ -627,7 +648,9 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": W,
-                "ms_per_step": ms / args.steps, "ms_per_step_median": median(per), "higher_is_better": True,
+                "ms_per_step": ms / args.steps, "ms_per_step_median": median(per),
+                "ms_per_step_p90_max": [sorted(per)[int(0.9 * (len(per) - 1))], max(per)],
+                "host_enqueue_ms_per_step": host_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": public_config(cfg, world, {
                     "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "

@@ -27,6 +27,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+
 #include "tma_common.cuh"
 
 namespace rslo {
@@ -53,26 +56,34 @@ struct ConvParams {
     int relu;
     int accumulate;                 // epilogue adds to the destination instead of overwriting it
     int stats_c, imgs_per_group;    // BN-statistics epilogue: channels of the stats table, images per statistics group
+    int hws[3][3];                  // halo variant: weight slice of tap (dh + 1, dw + 1)
 };
 
-template <int NT>
+// HALO variant (3x3, stride 1): a stage holds, for one column shift dw and one 32-channel chunk, the 8-wide x
+// (16 + 2)-high pixel patch ONCE (18 KB per plane) and the three weight slices of that column of taps; the three
+// row shifts dh are the same patch read from a start address 8 pixel rows (= one 1024-byte swizzle atom) further
+// down, so the activation is fetched 3 times per chunk instead of 9.
+constexpr int CV_HALO_W = 8, CV_HALO_H = 16;
+constexpr int CV_AH_BYTES = (CV_HALO_H + 2) * CV_HALO_W * CV_KS * 4;     // 18432
+
+template <int NT, bool HALO>
 struct CvCfg {
     static constexpr int B_BYTES = NT * CV_KS * 4;
-    static constexpr int STAGE_BYTES = 2 * CV_A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = NT >= 128 ? 3 : 4;
+    static constexpr int STAGE_BYTES = HALO ? 2 * CV_AH_BYTES + 6 * B_BYTES : 2 * CV_A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = HALO ? (NT >= 64 ? 2 : 3) : (NT >= 128 ? 3 : 4);
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
     static constexpr int TCOLS = 2 * NT < 32 ? 32 : 2 * NT;
 };
 
 __device__ __forceinline__ void drain_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int NT>
+template <int NT, bool HALO>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ ConvParams P, const float* __restrict__ bias, float* __restrict__ out,
             float* __restrict__ scratch, int* __restrict__ tile_counter, double* __restrict__ stats)
 {
-    using S = CvCfg<NT>;
+    using S = CvCfg<NT, HALO>;
     constexpr int STAGES = S::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -92,9 +103,11 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int rem = blockIdx.x - b * per_img;
     const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
     const int h0 = th * P.Ht, w0 = tw * P.Wt;
-    const int ntaps_mine = (P.ntaps - sidx + split - 1) / split;
-    const int nsteps = ntaps_mine * P.kchunks;
-    const int ngroups = (nsteps + P.group - 1) / P.group;
+    // work items of this CTA: taps x chunks (one stage each), or for HALO (column shift, chunk) pairs = 3 taps each
+    const int ntaps_mine = HALO ? 0 : (P.ntaps - sidx + split - 1) / split;
+    const int nsteps = HALO ? (3 * P.kchunks - sidx + split - 1) / split : ntaps_mine * P.kchunks;
+    const int group = HALO ? 1 : P.group;
+    const int ngroups = (nsteps + group - 1) / group;
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -126,6 +139,23 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             const uint32_t base = smem_u32(smem);
             int st = 0;
+            if constexpr (HALO) {
+                for (; st < nsteps; ++st) {
+                    const int item = sidx + st * split, dwi = item % 3, kc = item / 3;
+                    const int s = st % STAGES;
+                    mbar_wait(empty_bar + s, ((st / STAGES) & 1) ^ 1);
+                    const uint32_t a = base + s * S::STAGE_BYTES;
+                    tma::mbar_arrive_expect_tx(full_bar + s, S::STAGE_BYTES);
+                    tma::load_5d(a, &tmA, kc * CV_KS, w0 + dwi - 1, 0, h0 - 1, b, full_bar + s);
+                    tma::load_5d(a + CV_AH_BYTES, &tmA, kc * CV_KS, w0 + dwi - 1, 0, h0 - 1, b + P.nB, full_bar + s);
+                    const uint32_t bb = a + 2 * CV_AH_BYTES;
+#pragma unroll
+                    for (int dhi = 0; dhi < 3; ++dhi) {
+                        tma::load_3d(bb + dhi * S::B_BYTES, &tmW, kc * CV_KS, n0, P.hws[dhi][dwi], full_bar + s);
+                        tma::load_3d(bb + (3 + dhi) * S::B_BYTES, &tmW, kc * CV_KS, n0, P.hws[dhi][dwi] + P.nslices, full_bar + s);
+                    }
+                }
+            }
             for (int i = 0; i < ntaps_mine; ++i) {
                 const ConvTap tp = P.taps[sidx + i * split];
                 for (int kc = 0; kc < P.kchunks; ++kc, ++st) {
@@ -147,7 +177,35 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(NT);
             uint32_t acc = 0;
-            for (int st = 0; st < nsteps; ++st) {
+            if constexpr (HALO) {
+                for (int st = 0; st < nsteps; ++st) {
+                    const int buf = st & 1, s = st % STAGES;
+                    mbar_wait(tempty_bar + buf, ((st >> 1) & 1) ^ 1);
+                    mbar_wait(full_bar + s, (st / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d = tmem_base + buf * NT;
+                    const uint32_t sb = smem_u32(smem) + s * S::STAGE_BYTES;
+                    acc = 0;
+#pragma unroll
+                    for (int dhi = 0; dhi < 3; ++dhi) {
+                        const uint32_t a_hi = sb + dhi * (CV_HALO_W * CV_KS * 4), a_lo = a_hi + CV_AH_BYTES;
+                        const uint32_t b_hi = sb + 2 * CV_AH_BYTES + dhi * S::B_BYTES, b_lo = b_hi + 3 * S::B_BYTES;
+#pragma unroll
+                        for (int part = 0; part < 3; ++part) {        // lo*hi, hi*lo, hi*hi
+                            const uint32_t a = part == 0 ? a_lo : a_hi;
+                            const uint32_t bb = part == 1 ? b_lo : b_hi;
+#pragma unroll
+                            for (int kk = 0; kk < CV_KS / 8; ++kk) {
+                                umma_tf32(d, umma_desc_k_sw128(a + kk * 32), umma_desc_k_sw128(bb + kk * 32), idesc, acc);
+                                acc = 1;
+                            }
+                        }
+                    }
+                    umma_commit(empty_bar + s);
+                    umma_commit(tfull_bar + buf);
+                }
+            }
+            for (int st = 0; st < (HALO ? 0 : nsteps); ++st) {
                 const int grp = st / P.group, buf = grp & 1;
                 if (st - grp * P.group == 0) {
                     mbar_wait(tempty_bar + buf, ((grp >> 1) & 1) ^ 1);
@@ -317,18 +375,19 @@ static int encode_act(CUtensorMap* tm, const float* base, int B, int H, int W, i
     return tma::encode_f32(tm, base, 5, dims, strides, box, sw);
 }
 
-template <int NT>
+template <int NT, bool HALO>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvParams& P, int tiles, int split, int ntiles,
                        const float* bias, float* out, float* scratch, int* counter, double* stats, cudaStream_t st)
 {
-    using S = CvCfg<NT>;
+    using S = CvCfg<NT, HALO>;
     static bool configured = false;
     if (!configured) {
-        RSLO_CHECK(cudaFuncSetAttribute(k_conv2d_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        RSLO_CHECK(cudaFuncSetAttribute(k_conv2d_tc<NT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         configured = true;
     }
     RSLO_COUNT();
-    k_conv2d_tc<NT><<<dim3(tiles, split, ntiles), CV_THREADS, S::TOTAL, st>>>(tmA, tmW, P, bias, out, scratch, counter, stats);
+    k_conv2d_tc<NT, HALO><<<dim3(tiles, split, ntiles), CV_THREADS, S::TOTAL, st>>>(tmA, tmW, P, bias, out, scratch, counter,
+                                                                                 stats);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc");
     return 0;
 }
@@ -339,6 +398,16 @@ static int pick_nt(int N, int pixel_tiles)
     if (N % 64 == 0) return 64;
     if (N % 32 == 0) return 32;
     return 0;
+}
+// RSLO_CONV_HALO: 1 = always the halo variant where it applies, 0 = never, unset = measure both once per layer shape
+static int conv_halo_mode()
+{
+    static int v = -2;
+    if (v == -2) {
+        const char* e = getenv("RSLO_CONV_HALO");
+        v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+    }
+    return v;
 }
 static int conv_drain_group()
 {
@@ -364,10 +433,22 @@ constexpr int CV_MAX_COUNTERS = 4096;
 // Generic implicit-GEMM launch: A = split-pair activation [2][B][H][W][C] viewed with parity factor Pf,
 // weight image [2][nslices][N][C], output pixel grid gridH x gridW per image (tile coordinates),
 // taps in tile coordinates, output address mapping (OH, OW, osh, ooh, osw, oow, ldo).
-static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, const float* wimg, int nslices, int N,
-                    int gridH, int gridW, const ConvTap* taps, int ntaps, float* out, int OH, int OW, int osh, int ooh,
-                    int osw, int oow, int ldo, const float* bias, int relu, void* ws, size_t ws_bytes, cudaStream_t st,
-                    double* stats = nullptr, int imgs_per_group = 1, int accumulate = 0)
+static bool halo_eligible(int Pf, const ConvTap* taps, int ntaps)
+{
+    if (Pf != 1 || ntaps != 9) return false;
+    int seen = 0;
+    for (int i = 0; i < 9; ++i) {
+        const ConvTap& t = taps[i];
+        if (t.coff != 0 || t.p != 0 || t.dw < -1 || t.dw > 1 || t.dh < -1 || t.dh > 1) return false;
+        seen |= 1 << ((t.dh + 1) * 3 + t.dw + 1);
+    }
+    return seen == 0x1ff;
+}
+
+static int run_conv_impl(bool halo, const float* a_split, int B, int H, int W, int C, int Pf, const float* wimg, int nslices,
+                         int N, int gridH, int gridW, const ConvTap* taps, int ntaps, float* out, int OH, int OW, int osh,
+                         int ooh, int osw, int oow, int ldo, const float* bias, int relu, void* ws, size_t ws_bytes,
+                         cudaStream_t st, double* stats, int imgs_per_group, int accumulate)
 {
     if (C % 32 != 0 || ntaps < 1 || ntaps > CV_MAX_TAPS || (H % Pf) || (W % Pf)) {
         set_last_error("rslo_conv2d_tc: unsupported shape", cudaErrorInvalidValue);
@@ -375,18 +456,35 @@ static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, co
     }
     ConvParams P;
     memset(&P, 0, sizeof P);
-    pick_tile(gridW, gridH, CV_ROWS, &P.Wt, &P.Ht);
+    // 3x3 / stride 1 (forward, and the data gradient of such a layer): halo variant, see CvCfg
+    if (halo) {
+        for (int i = 0; i < 9; ++i) P.hws[taps[i].dh + 1][taps[i].dw + 1] = taps[i].wslice;
+        P.Wt = CV_HALO_W;
+        P.Ht = CV_HALO_H;
+    } else {
+        pick_tile(gridW, gridH, CV_ROWS, &P.Wt, &P.Ht);
+    }
     P.wt_log2 = ilog2(P.Wt);
     P.tiles_w = cdiv(gridW, P.Wt);
     P.tiles_h = cdiv(gridH, P.Ht);
     const int tiles = B * P.tiles_w * P.tiles_h;
-    const int NT = pick_nt(N, tiles);
+    int NT = pick_nt(N, tiles);
     if (NT == 0) {
         set_last_error("rslo_conv2d_tc: output channels must be a multiple of 32", cudaErrorInvalidValue);
         return (int)cudaErrorInvalidValue;
     }
+    if (halo && NT > 64) NT = 64;                        // three weight slices per stage: 64 output channels fit
     const int ntiles = N / NT;
     int split = pick_split(tiles * ntiles, ntaps);
+    if (halo) {                                          // work items = (column shift, chunk) pairs
+        const int items = 3 * (C / CV_KS);
+        split = 1;
+        for (int d = items; d > 1; --d)
+            if (items % d == 0 && (long)tiles * ntiles * d <= 160) {
+                split = d;
+                break;
+            }
+    }
     for (int i = 0; i < ntaps; ++i) P.taps[i] = taps[i];
     P.ntaps = ntaps;
     P.kchunks = C / CV_KS;
@@ -415,7 +513,7 @@ static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, co
         }
     }
     CUtensorMap tmA, tmW;
-    int rc = encode_act(&tmA, a_split, B, H, W, C, Pf, P.Wt, P.Ht, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_act(&tmA, a_split, B, H, W, C, Pf, P.Wt, halo ? P.Ht + 2 : P.Ht, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     {
         const uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)2 * nslices};
@@ -424,9 +522,72 @@ static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, co
         rc = tma::encode_f32(&tmW, wimg, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    if (NT == 128) return launch_conv<128>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
-    if (NT == 64) return launch_conv<64>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
-    return launch_conv<32>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+    if (halo) {
+        if (NT == 64) return launch_conv<64, true>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+        return launch_conv<32, true>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+    }
+    if (NT == 128) return launch_conv<128, false>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+    if (NT == 64) return launch_conv<64, false>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+    return launch_conv<32, false>(tmA, tmW, P, tiles, split, ntiles, bias, out, scratch, counter, stats, st);
+}
+
+// Which variant runs a 3x3 / stride-1 layer: fewer activation bytes (halo) usually wins, but wide data gradients
+// (N >= 256: many 64-channel tiles re-reading the patch) can favour the plain tiling with its deeper pipeline.  Each layer
+// shape is measured once (both variants, CUDA events on the launching stream, first non-accumulating call outside graph
+// capture) and the choice cached for the life of the process.
+struct TuneKey {
+    int v[8];
+    bool operator<(const TuneKey& o) const { return memcmp(v, o.v, sizeof v) < 0; }
+};
+static std::map<TuneKey, int> g_conv_choice;
+static std::mutex g_conv_mutex;
+
+static int run_conv(const float* a_split, int B, int H, int W, int C, int Pf, const float* wimg, int nslices, int N,
+                    int gridH, int gridW, const ConvTap* taps, int ntaps, float* out, int OH, int OW, int osh, int ooh,
+                    int osw, int oow, int ldo, const float* bias, int relu, void* ws, size_t ws_bytes, cudaStream_t st,
+                    double* stats = nullptr, int imgs_per_group = 1, int accumulate = 0)
+{
+#define RUN(h, o_stats, o_acc)                                                                                              \
+    run_conv_impl(h, a_split, B, H, W, C, Pf, wimg, nslices, N, gridH, gridW, taps, ntaps, out, OH, OW, osh, ooh, osw, oow,  \
+                  ldo, bias, relu, ws, ws_bytes, st, o_stats, imgs_per_group, o_acc)
+    const int mode = conv_halo_mode();
+    if (mode == 0 || C % 32 != 0 || !halo_eligible(Pf, taps, ntaps)) return RUN(false, stats, accumulate);
+    if (mode == 1) return RUN(true, stats, accumulate);
+    const TuneKey key = {{B, H, W, C, N, gridH, gridW, ws != nullptr}};
+    int choice = -1;
+    {
+        std::lock_guard<std::mutex> lock(g_conv_mutex);
+        auto it = g_conv_choice.find(key);
+        if (it != g_conv_choice.end()) choice = it->second;
+    }
+    if (choice < 0) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (cap != cudaStreamCaptureStatusNone || accumulate) return RUN(N <= 128, stats, accumulate);   // not measurable now
+        cudaEvent_t ev[3];
+        for (auto& e : ev) RSLO_CHECK(cudaEventCreate(&e));
+        float ms[2] = {0.f, 0.f};
+        for (int h = 0; h < 2; ++h) {
+            int rc = RUN(h == 1, nullptr, 0);                              // warm (tensor maps, instruction cache)
+            if (rc) return rc;
+            RSLO_CHECK(cudaEventRecord(ev[h], st));
+            for (int i = 0; i < 3; ++i)
+                if ((rc = RUN(h == 1, nullptr, 0))) return rc;
+            RSLO_CHECK(cudaEventRecord(ev[h + 1], st));
+            if (h == 0) {                                                  // ev[1] is reused as the second start
+                RSLO_CHECK(cudaEventSynchronize(ev[1]));
+                RSLO_CHECK(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
+            }
+        }
+        RSLO_CHECK(cudaEventSynchronize(ev[2]));
+        RSLO_CHECK(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));
+        for (auto& e : ev) cudaEventDestroy(e);
+        choice = ms[1] < 0.97f * ms[0] ? 1 : 0;
+        std::lock_guard<std::mutex> lock(g_conv_mutex);
+        g_conv_choice[key] = choice;
+    }
+    return RUN(choice == 1, stats, accumulate);
+#undef RUN
 }
 
 // forward taps of a ks x ks / stride s / pad (ks/2) convolution read through the parity view (Pf = s)

@@ -50,28 +50,61 @@ def _enqueue_frame_tables(indices, n, sparse_shape, table0, caps, n_dev=None):
     return lv, raw
 
 
+class PendingTables:
+    """Index tables of T frames that have been ENQUEUED (capacity-sized, row counts still on the device) together with
+    the asynchronous device->host copy of every count.  `finish()` waits for that copy (a no-op wait when it is called a
+    step later), retries the rare frame whose level outgrew its capacity, and returns per frame
+    (levels, raw tables, row counts per level).  Splitting the two lets `net.prepare()` return without blocking the
+    training thread on the preparation stream."""
+
+    def __init__(self, frames, sparse_shape):
+        self.frames, self.sparse_shape = frames, sparse_shape
+        self.pend = [_enqueue_frame_tables(idx, n, sparse_shape, tab, None, nd) for idx, n, tab, nd in frames]
+        self.dev = frames[0][0].device
+        self.counts_dev = torch.stack([self._counts_of(lv, fr[3], fr[1]) for (lv, _), fr in zip(self.pend, frames)])
+        self.counts_host = torch.empty(self.counts_dev.shape, dtype=torch.int32, pin_memory=self.dev.type == "cuda")
+        self.counts_host.copy_(self.counts_dev, non_blocking=True)
+        self.event = None
+        if self.dev.type == "cuda":
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(self.dev))
+
+    def _counts_of(self, lv, nd, n):
+        n0 = nd.reshape(1).to(torch.int32) if nd is not None else torch.tensor([n], dtype=torch.int32, device=self.dev)
+        return torch.cat([torch.stack([n0[0], n0[0]])[None], torch.stack([l["ndev2"] for l in lv[1:]])])
+
+    def device_tensors(self):
+        """every tensor the enqueue step allocated (for record_stream when it ran on a side stream)"""
+        out = [self.counts_dev]
+        for lv, raw in self.pend:
+            for l in lv:
+                out += [l["idx"], l.get("ndev"), l.get("ndev2"), l["tab"].cells, l["tab"].perm]
+            for v in raw.values():
+                out += list(v) if isinstance(v, tuple) else [v]
+        return [t for t in out if t is not None]
+
+    def finish(self):
+        if self.event is not None:
+            self.event.synchronize()
+        counts = self.counts_host.numpy()
+        out = []
+        for f, (lv, raw) in enumerate(self.pend):
+            c = counts[f]
+            fr = self.frames[f]
+            while not (c[1:, 1] <= [l["cap"] for l in lv[1:]]).all():       # rare: a level grew; redo this frame
+                caps = [max(int(v), 1) * 2 for v in c[1:, 1]]
+                lv, raw = _enqueue_frame_tables(fr[0], fr[1], self.sparse_shape, fr[2], caps, fr[3])
+                c = self._counts_of(lv, fr[3], fr[1]).cpu().numpy()
+            out.append((lv, raw, [int(v) for v in c[:, 0]]))
+        return out
+
+
 def _frames_tables(frames, sparse_shape):
     """frames: list of (indices, n, table0, n_dev): n rows are live, or - when n_dev (device int) is given -
     n is only the capacity and the live count is still on the device (voxeliser output that has not been
     synchronised).  All frames are enqueued first and ONE device->host copy brings back every count.
     -> per frame (levels, raw tables, row counts per level)."""
-    pend = [_enqueue_frame_tables(idx, n, sparse_shape, tab, None, nd) for idx, n, tab, nd in frames]
-    dev = frames[0][0].device
-
-    def counts_of(lv, nd, n):
-        n0 = nd.reshape(1).to(torch.int32) if nd is not None else torch.tensor([n], dtype=torch.int32, device=dev)
-        return torch.cat([torch.stack([n0[0], n0[0]])[None], torch.stack([l["ndev2"] for l in lv[1:]])])
-
-    counts = torch.stack([counts_of(lv, fr[3], fr[1]) for (lv, _), fr in zip(pend, frames)]).cpu().numpy()
-    out = []
-    for f, (lv, raw) in enumerate(pend):
-        c = counts[f]
-        while not (c[1:, 1] <= [l["cap"] for l in lv[1:]]).all():       # rare: a level grew; redo this frame
-            caps = [max(int(v), 1) * 2 for v in c[1:, 1]]
-            lv, raw = _enqueue_frame_tables(frames[f][0], frames[f][1], sparse_shape, frames[f][2], caps, frames[f][3])
-            c = counts_of(lv, frames[f][3], frames[f][1]).cpu().numpy()
-        out.append((lv, raw, [int(v) for v in c[:, 0]]))
-    return out
+    return PendingTables(frames, sparse_shape).finish()
 
 
 def build_frame_tables(indices, n, sparse_shape, table0=None):
@@ -79,10 +112,10 @@ def build_frame_tables(indices, n, sparse_shape, table0=None):
     return build_tables_batched([(indices, n, table0, None)], sparse_shape)[0]
 
 
-def build_tables_batched(frames, sparse_shape):
+def build_tables_batched(frames, sparse_shape, pending=None):
     """Index tables for T frames that share one pass through the encoder: per-frame tables are appended
     row-wise (row indices of frame f shifted by the rows before it).  -> ({indice_key: IndexEntry}, meta)."""
-    per = _frames_tables(frames, sparse_shape)
+    per = pending.finish() if pending is not None else _frames_tables(frames, sparse_shape)
     T = len(per)
     ns = [[p[2][l] for p in per] for l in range(5)]                    # rows per level per frame
     offs = [[int(sum(ns[l][:f])) for f in range(T)] for l in range(5)]
@@ -183,13 +216,27 @@ class SpMiddleFHDWithCov2_3(nn.Module):
         T = len(voxel_features)
         tables = tables if tables is not None else [None] * T
         n_devs = n_devs if n_devs is not None else [None] * T
+        return self.prepare_frames_begin(voxel_features, coors, tables, n_devs)()
+
+    def prepare_frames_begin(self, voxel_features, coors, tables=None, n_devs=None):
+        """Enqueue the table kernels and the asynchronous copy of the row counts; -> a callable that finishes the job
+        (waits for the counts, appends the frames' tables, trims the inputs) and returns what prepare_frames returns.
+        The callable carries `.pending` (PendingTables)."""
+        T = len(voxel_features)
+        tables = tables if tables is not None else [None] * T
+        n_devs = n_devs if n_devs is not None else [None] * T
         coors = [c.int().contiguous() for c in coors]
         shape = [int(s) for s in self.sparse_shape]
         frames = [(coors[t], int(voxel_features[t].shape[0]), tables[t], n_devs[t]) for t in range(T)]
-        entries, meta = build_tables_batched(frames, shape)
-        feats = [voxel_features[t][:meta["rows"][0][t]] for t in range(T)]
-        coors = [coors[t][:meta["rows"][0][t]] for t in range(T)]
-        return {"entries": entries, "meta": meta, "features": feats, "coors": coors}
+        pending = PendingTables(frames, shape)
+
+        def finish():
+            entries, meta = build_tables_batched(frames, shape, pending)
+            feats = [voxel_features[t][:meta["rows"][0][t]] for t in range(T)]
+            cs = [coors[t][:meta["rows"][0][t]] for t in range(T)]
+            return {"entries": entries, "meta": meta, "features": feats, "coors": cs}
+        finish.pending = pending
+        return finish
 
     def forward_frames(self, voxel_features, coors, batch_size, tables=None, n_devs=None, prepared=None):
         """The reference calls the encoder once per frame (`voxel_odom_net.py:423-428`); here the T frames

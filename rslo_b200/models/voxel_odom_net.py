@@ -54,25 +54,6 @@ def create_cycle_constraint_data(xs, cat_dim=1):
     return [torch.stack(x1, dim=cat_dim).reshape(-1, *shape[1:]), torch.stack(x2, dim=cat_dim).reshape(-1, *shape[1:])]
 
 
-def _record_stream_tree(obj, stream, _seen=None):
-    """Tell the caching allocator that every tensor reachable from `obj` is also used on `stream`."""
-    _seen = set() if _seen is None else _seen
-    if id(obj) in _seen or obj is None:
-        return
-    _seen.add(id(obj))
-    if isinstance(obj, torch.Tensor):
-        if obj.is_cuda:
-            obj.record_stream(stream)
-    elif isinstance(obj, dict):
-        for v in obj.values():
-            _record_stream_tree(v, stream, _seen)
-    elif isinstance(obj, (list, tuple)):
-        for v in obj:
-            _record_stream_tree(v, stream, _seen)
-    elif hasattr(obj, "__dict__") and not isinstance(obj, (torch.nn.Module, torch.cuda.Stream, torch.cuda.Event)):
-        _record_stream_tree(vars(obj), stream, _seen)
-
-
 class _LazyOutputs(dict):
     """Output dict whose display-only entries are computed when somebody reads them (`ret["feature_mask"]`)."""
     lazy = {}
@@ -277,12 +258,24 @@ class UnVoxelOdomNetICP3(nn.Module):
                 coors.append(c)
                 tables.append(tab)
                 n_devs.append(nd)
-            prep = self.middle_feature_extractor.prepare_frames(voxels, coors, tables, n_devs)
+            finish = self.middle_feature_extractor.prepare_frames_begin(voxels, coors, tables, n_devs)
             ev = torch.cuda.Event()
             ev.record(st)
-        _record_stream_tree([prep, pts, voxels, coors], main)
+        # everything above was allocated on the preparation stream and will be read on the caller's stream
+        made = list(pts) + voxels + coors + [t for t in n_devs if t is not None] + finish.pending.device_tensors()
+        for tab in tables:
+            if tab is not None:
+                made += [tab.cells, tab.perm]
+        seen = set()
+        for t in made:
+            if t is not None and t.is_cuda and id(t) not in seen:
+                seen.add(id(t))
+                t.record_stream(main)
         out = dict(example)
-        out["_prepared"] = {"frames": prep, "event": ev}
+        # the row counts come back asynchronously: the tables are appended (and the step blocks on the counts, normally
+        # long since there) when the prepared example is used, `finish()` in forward
+        out["_prepared"] = {"finish": finish, "event": ev, "made": [t for t in made if t is not None and t.is_cuda],
+                            "stream": main.cuda_stream}
         return out
 
     def network_forward(self, voxels, num_points, coors, batch_size, example):
@@ -348,8 +341,13 @@ class UnVoxelOdomNetICP3(nn.Module):
             invalidate_weight_images()      # weights move every step, possibly through .data
         if "_prepared" in example:
             prep = example["_prepared"]
-            torch.cuda.current_stream().wait_event(prep["event"])
-            _record_stream_tree(prep["frames"], torch.cuda.current_stream())
+            cur = torch.cuda.current_stream()
+            cur.wait_event(prep["event"])
+            if cur.cuda_stream != prep["stream"]:        # used on another stream than prepare() was told about
+                for t in prep["made"]:
+                    t.record_stream(cur)
+            if "frames" not in prep:                     # first use: counts -> appended tables (on this stream)
+                prep["frames"] = prep.pop("finish")()
             example = dict(example)
             example["_prepared_frames"] = prep["frames"]
             voxels, coors = prep["frames"]["features"], prep["frames"]["coors"]

@@ -22,7 +22,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor",
         "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.sum", "l1tex__t_bytes.sum", "sm__cycles_elapsed.max"]
+        "smsp__inst_executed.sum", "l1tex__t_bytes.sum", "sm__cycles_elapsed.max",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "sm__inst_executed_pipe_uniform.sum", "smsp__cycles_active.avg", "sm__cycles_active.avg"]
 
 
 def short(name):
@@ -66,20 +68,25 @@ def launches(rnd):
 
 
 def reports(rnd):
+    """prof_<round>_<name>.ncu-rep (read with ncu here) or prof_<round>_<name>.raw.csv (already exported on the GPU
+    box with `ncu -i ... --page raw --csv`: the reports themselves exceed what gpurun brings back)."""
     for fn in sorted(os.listdir(SRC)):
-        m = re.match(rf"prof_{rnd}_(.+)\.ncu-rep$", fn)
+        m = re.match(rf"prof_{rnd}_(.+?)(\.ncu-rep|\.raw\.csv)$", fn)
         if not m:
             continue
-        raw = subprocess.run(["ncu", "-i", os.path.join(SRC, fn), "--page", "raw", "--csv"], capture_output=True,
-                             text=True).stdout
+        if fn.endswith(".ncu-rep"):
+            raw = subprocess.run(["ncu", "-i", os.path.join(SRC, fn), "--page", "raw", "--csv"], capture_output=True,
+                                 text=True).stdout
+        else:
+            raw = open(os.path.join(SRC, fn)).read()
         rows = list(csv.reader(raw.splitlines()))
         if len(rows) < 3:
             continue
         hdr, units, data = rows[0], rows[1], rows[2:]
         with open(os.path.join(OUT, f"{rnd}_{m.group(1)}_ncu.md"), "w") as f:
             f.write(f"# ncu --set full: `{m.group(1)}` ({rnd})\n\n")
-            f.write("Captured inside `bench.py --steps 1 --warmup 3 --pairs-per-gpu 1` (`--clock-control none "
-                    "--import-source on --profile-from-start off`); one column per captured launch.\n\n")
+            f.write("Captured inside `bench.py --steps 1 --warmup 3` (the bench's train step, 2 pairs per GPU; "
+                    "`--clock-control none --import-source on --profile-from-start off`); one column per captured launch.\n\n")
             f.write("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n")
             f.write("|---|---|" + "---:|" * len(data) + "\n")
             kn = hdr.index("Kernel Name")
