@@ -322,6 +322,7 @@ class Runner:
             from rslo_b200.data.prefetch import PreparedPrefetcher
             self.prefetcher = PreparedPrefetcher(net, dev)
         self.host_s = 0.0
+        self.host_phase = {"forward": 0.0, "backward": 0.0, "prepare": 0.0, "reduce+optimizer": 0.0, "steps": 0}
 
     def prepared_step(self, i, from_host):
         """net.prepare(): voxelisation + index tables of ALL samples of step i on a side stream (the reference does
@@ -349,9 +350,15 @@ class Runner:
             ex = self.prepared_step(i, from_host)
         if hasattr(ex, "result"):
             ex = ex.result()
+        ph = self.host_phase
+        t0 = time.perf_counter()
         if self.train:
             ret = net(ex)
+            t1 = time.perf_counter()
             ret["loss"].sum().backward()
+            t2 = time.perf_counter()
+            ph["forward"] += t1 - t0
+            ph["backward"] += t2 - t1
             res = ret["loss"].detach().reshape(-1)
         else:
             with torch.no_grad():
@@ -360,12 +367,17 @@ class Runner:
         # the next step's samples are prepared while this one's kernels run
         for stale in [k for k in self.prefetch if k[1] != from_host or k[0] <= i]:
             del self.prefetch[stale]
+        t3 = time.perf_counter()
         for ahead in range(1, self.PREFETCH_DEPTH + 1):
             if (i + ahead, from_host) not in self.prefetch:
                 self.prefetch[(i + ahead, from_host)] = self.prepared_step(i + ahead, from_host)
+        t4 = time.perf_counter()
+        ph["prepare"] += t4 - t3
         if self.train:
             self.reducer.all_reduce(average=False)  # pack into the flat buffer (+ NCCL all-reduce when N > 1)
             self.opt.step()                         # global-norm clip + 1/world + weight decay + Adam: 2 launches
+            ph["reduce+optimizer"] += time.perf_counter() - t4
+        ph["steps"] += 1
         if from_host:
             r = res.cpu()                                                  # D2H of the step's result
             self.d2h_bytes += r.numel() * 4
@@ -380,6 +392,8 @@ class Runner:
         torch.cuda.synchronize()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]
         evs[0].record()
+        for k in self.host_phase:
+            self.host_phase[k] = 0
         t_host = time.time()
         for i in range(nsteps):
             self.flush.zero_()                                             # L2 flush between steps
@@ -579,6 +593,7 @@ def main():
     launches = K.kernel_launch_count() - l0
     run_train = run.train
     host_ms = 1e3 * run.host_s / args.steps
+    host_phase = {k: 1e3 * v / max(run.host_phase["steps"], 1) for k, v in run.host_phase.items() if k != "steps"}
     clocks = sampler.stop() if rank == 0 else None
     value = world * ppg * args.steps / (ms / 1e3)
 
@@ -590,7 +605,9 @@ def main():
     e2e = {"value": world * ppg * args.steps / (ms_e2e / 1e3), "unit": "pairs/s",
            "h2d_bytes_per_step": run.h2d_bytes // (args.steps + run.PREFETCH_DEPTH),
            "d2h_bytes_per_step": run.d2h_bytes // args.steps,
-           "ms_per_step": ms_e2e / args.steps, "ms_per_step_median": median(per_e2e)}
+           "ms_per_step": ms_e2e / args.steps, "ms_per_step_median": median(per_e2e),
+           "host_phase_ms_per_step": {k: 1e3 * v / max(run.host_phase["steps"], 1) for k, v in run.host_phase.items()
+                                      if k != "steps"}}
 
     # rooflines: profiled replica of the timed steps (every rank runs it: its steps contain the collective)
     roofline = roofline_hbm = breakdown = None
@@ -650,7 +667,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms / args.steps, "ms_per_step_median": median(per),
                 "ms_per_step_p90_max": [sorted(per)[int(0.9 * (len(per) - 1))], max(per)],
-                "host_enqueue_ms_per_step": host_ms, "higher_is_better": True,
+                "host_enqueue_ms_per_step": host_ms, "host_phase_ms_per_step": host_phase, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": public_config(cfg, world, {
                     "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
