@@ -352,6 +352,18 @@ int rslo_bn1d_seg_backward(const float* dz, const float* x, int C, const int* se
                            const float* gamma, const float* beta, float slope, int batch_stats, double* sums, float* dx,
                            float* dgamma, float* dbeta, rslo_stream_t stream);
 
+/* ---- a13 glue: predicted pose applied to the target frame (csrc/pair_transform.cu) -----------------------------
+ * y [n,3] = x @ R(q)^T + t with kornia 0.4.0's quaternion_to_rotation_matrix (q given as (w,x,y,z), normalised with
+ * eps 1e-12), replacing the torch chain at rslo/models/voxel_odom_net.py:671-690; x rows are ldx floats apart (the
+ * xyz columns of the voxel features).  identity != 0: R = I, t = 0 (global step <= 1500, :677-679).  R_out [9]
+ * receives R.  Backward: grad_y, x -> dq (w,x,y,z) [4], dt [3]; workspace: rslo_pair_transform_workspace_bytes(),
+ * ZEROED once by the caller (left zeroed). */
+size_t rslo_pair_transform_workspace_bytes(void);
+int rslo_pair_transform_forward(const float* x, int ldx, int n, const float* q_wxyz, const float* t, int identity, float* y,
+                                float* R_out, rslo_stream_t stream);
+int rslo_pair_transform_backward(const float* grad_y, const float* x, int ldx, int n, const float* q_wxyz, float* dq_wxyz,
+                                 float* dt, void* workspace, size_t workspace_bytes, rslo_stream_t stream);
+
 /* ---- f-N2: the optimizer step in two launches (csrc/optim.cu) --------------------------------------------
  * Replaces torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0) (train_hdf5.py:671) followed by
  * OptimWrapper.step() (rslo/torchplus/train/fastai_optim.py:181-194: p *= 1 - wd*lr on every trainable parameter,

@@ -7,12 +7,8 @@ __version__ = "0.1.0"
 
 import os as _os
 
-import torch as _torch
-
-# The reference computes this path in FP32 (torch 1.2 had no TF32); cuDNN's TF32 convolutions give
-# ~1e-3 pose error on B200, outside the path's 1e-4 relative parity bound, in forward AND backward.
-_torch.backends.cudnn.allow_tf32 = False
-_torch.backends.cuda.matmul.allow_tf32 = False
+# No process-wide backend switches here: the path's own kernels are FP32-exact by construction (split-TF32),
+# torch's matmul TF32 is off by default, and the cuDNN A/B trunk scopes its flags itself (models/odom_pred.py).
 
 DEFAULT_CONFIG = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "config", "kitti_ours.prototxt")
 
@@ -25,10 +21,14 @@ def build_network(config_path=None, testing=False, measure_time=False, seed=None
     from .builder import second_builder, voxel_builder
     cfg = _config.load(config_path or DEFAULT_CONFIG)
     vg = voxel_builder.build(cfg.model.second.voxel_generator)
-    try:        # preprocess.max_number_of_voxels of the input reader (dataset_builder.py:78, preprocess.py:493)
-        vg.max_voxels_per_call = int(cfg.train_input_reader.preprocess.max_number_of_voxels)
-    except AttributeError:
-        pass
+    # preprocess.max_number_of_voxels of the input reader that feeds this net (dataset_builder.py:78, preprocess.py:493):
+    # the eval reader's when testing (evaluate.py builds its dataset from eval_input_reader), else the train reader's
+    for reader in (("eval_input_reader", "train_input_reader") if testing else ("train_input_reader", "eval_input_reader")):
+        try:
+            vg.max_voxels_per_call = int(getattr(cfg, reader).preprocess.max_number_of_voxels)
+            break
+        except (AttributeError, TypeError):
+            continue
     if seed is not None:
         torch.manual_seed(seed)
     net = second_builder.build(cfg.model.second, vg, measure_time=measure_time, testing=testing)

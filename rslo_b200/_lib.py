@@ -85,6 +85,9 @@ SIGNATURES = {
     "rslo_dense_backward": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rslo_bn1d_seg_forward": (_i, [_vp, _i, C.POINTER(_i), _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _vp, _vp, _vp, _vp]),
     "rslo_bn1d_seg_backward": (_i, [_vp, _vp, _i, C.POINTER(_i), _i, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rslo_pair_transform_workspace_bytes": (_sz, []),
+    "rslo_pair_transform_forward": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rslo_pair_transform_backward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rslo_grad_norm_workspace_bytes": (_sz, []),
     "rslo_grad_sumsq": (_i, [_vp, _sz, _vp, _vp, _sz, _vp]),
     "rslo_adam_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _vp]),

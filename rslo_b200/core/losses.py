@@ -26,9 +26,10 @@ class Loss(nn.Module):
         if ignore_nan_targets:
             target_tensor = torch.where(torch.isnan(target_tensor), prediction_tensor, target_tensor)
         ret = self._compute_loss(prediction_tensor, target_tensor, **params)
+        w = self._loss_weight
         if isinstance(ret, (list, tuple)):
-            return [self._loss_weight * ret[0]] + list(ret[1:])
-        return self._loss_weight * ret     # the reference evaluates _compute_loss a second time here
+            return [ret[0] if w == 1 else w * ret[0]] + list(ret[1:])     # (x * 1.0 is exact: skip the launch)
+        return ret if w == 1 else w * ret     # the reference evaluates _compute_loss a second time here
 
 
 class AdaptiveWeightedL2Loss(Loss):

@@ -742,3 +742,50 @@ def bn1d_seg_backward(dz, x, seg, mean_rstd, gamma, beta, slope, batch_stats):
                                      stream()), "rslo_bn1d_seg_backward")
     _count(2)
     return dx, dgb[0], dgb[1]
+
+
+# ------------------------------------------------------------------------------------------------
+# a13 glue: predicted pose applied to the target frame's points (csrc/pair_transform.cu)
+# ------------------------------------------------------------------------------------------------
+_PX_WS = {}
+
+
+class _PairTransformFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, q_wxyz, t, identity):
+        # x: [n, >=3] rows (xyz first), may be a row-strided view of the voxel features
+        assert x.dtype == torch.float32 and x.is_cuda and x.stride(1) == 1
+        n, ldx = x.shape[0], x.stride(0)
+        q = q_wxyz.detach().reshape(4).contiguous()
+        tt = t.detach().reshape(3).contiguous()
+        y = torch.empty((n, 3), dtype=torch.float32, device=x.device)
+        R = torch.empty((3, 3), dtype=torch.float32, device=x.device)
+        check(lib.rslo_pair_transform_forward(ptr(x), ldx, n, ptr(q), ptr(tt), 1 if identity else 0, ptr(y), ptr(R), stream()),
+              "rslo_pair_transform_forward")
+        _count()
+        ctx.identity, ctx.qshape, ctx.tshape = identity, q_wxyz.shape, t.shape
+        ctx.save_for_backward(x, q)
+        ctx.mark_non_differentiable(R)
+        return y, R
+
+    @staticmethod
+    def backward(ctx, gy, _gR):
+        if ctx.identity:
+            return None, None, None, None
+        x, q = ctx.saved_tensors
+        key = raw_stream()
+        ws = _PX_WS.get(key)
+        if ws is None:
+            ws = _PX_WS[key] = torch.zeros(lib.rslo_pair_transform_workspace_bytes(), dtype=torch.uint8, device=x.device)
+        out = torch.empty(7, dtype=torch.float32, device=x.device)
+        gy = _f32(gy.contiguous())
+        check(lib.rslo_pair_transform_backward(ptr(gy), ptr(x), x.stride(0), x.shape[0], ptr(q), ptr(out), ptr(out[4:]), ptr(ws),
+                                               ws.numel(), stream()), "rslo_pair_transform_backward")
+        _count()
+        return None, out[:4].reshape(ctx.qshape), out[4:].reshape(ctx.tshape), None
+
+
+def pair_transform(x, q_wxyz, t, identity=False):
+    """(y [n,3] = x[:, :3] @ R(q)^T + t, R [3,3]); differentiable w.r.t. q (w,x,y,z) and t; x is treated as data
+    (the reference detaches nothing here, but the points are encoder INPUTS without gradient)."""
+    return _PairTransformFn.apply(x, q_wxyz, t, bool(identity))

@@ -5,6 +5,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .. import kernels as K
+from ..layers import encoder_engine
 from ..layers import sparse3d as spconv
 from ..layers.sparse3d import IndexEntry
 from ..torchplus import Empty, change_default_args
@@ -257,10 +258,19 @@ class SpMiddleFHDWithCov2_3(nn.Module):
                                       table=entries["subm0"].out_table)
         ret.indice_dict = entries
         ret.seg, ret.frames = meta["rows"][0], meta["frames0"]
-        ret0 = self.middle_conv(ret)
-        ret = self.middle_conv_tail(ret0)
-        cov_pred = self.middle_cov_deconv(ret0)
-        cov = cov_pred.features
+        if encoder_engine.USE_ENGINE and feats.is_cuda:
+            # one autograd node for the 25 layers (layers/encoder_engine.py): same kernels, a fraction of the host time
+            eng = self.__dict__.get("_engine")
+            if eng is None:
+                eng = self.__dict__["_engine"] = encoder_engine.SparseEncoderEngine(self)
+            tail, cov = encoder_engine.encode(eng, feats, entries, meta["rows"][0])
+            e5 = entries["conv3d5"]
+            ret = spconv.SparseConvTensor(tail, None, e5.out_shape, batch_size)
+            ret.n, ret.seg, ret.frames = e5.n_out, e5.seg_out, e5.out_frames
+        else:
+            ret0 = self.middle_conv(ret)
+            ret = self.middle_conv_tail(ret0)
+            cov = self.middle_cov_deconv(ret0).features
         cov = torch.cat([F.elu(cov[:, :3]) + 1 + 1e-6, cov[:, 3:]], dim=1)     # middle.py:237
         covs = [cov] if T == 1 else list(torch.split(cov, meta["rows"][0]))
         return ret.dense_frames(), covs, voxel_features, coors

@@ -479,7 +479,25 @@ class UnVoxelOdomNetICP3(nn.Module):
             weights = [0.01, 0.01, 0.05, 0.1, 1]
             res_rs, res_ts = [], []
             # the samples of a step are independent: each keeps its own common point count (voxel_odom_net.py:646-651)
-            for smp in range(S):
+            # two-frame samples (the shipped training / evaluation setup): the pair's tensors are views of the frames'
+            # rows and the predicted pose is applied by one kernel (csrc/pair_transform.cu) instead of ~80 torch ops
+            fast = (T == 2 and len(rotation_preds) == 1 and rotation_preds[0].shape[-1] == 4 and feats[0].shape[1] > 6
+                    and feats[0].is_cuda)
+            for smp in range(S if fast else 0):
+                f0, f1 = feats[smp * T], feats[smp * T + 1]
+                c0, c1 = preds_dict["middle_conf_preds"][smp * T], preds_dict["middle_conf_preds"][smp * T + 1]
+                n = min(f0.shape[0], f1.shape[0])
+                p0, p1 = f0[:n], f1[:n]
+                target, R_pred = K.pair_transform(p1, rotation_preds[0][smp], translation_preds[0][smp],
+                                                  identity=step <= 1500)
+                icp_iter = self.icp_iter if step > 1500 else 5
+                l, res_r, res_t = consistency_loss(
+                    p0[None, :, :3], target[None], cov_pred=c0[None, :n], cov_target=c1[None, :n], R_pred=R_pred[None],
+                    t_pred=None, normal_pred=p0[None, :, 4:7], normal_target=None, mask=None, icp_iter=icp_iter)
+                C_loss = C_loss + l * ((1 - warm_weight) * weights[-1] / S)
+                res_rs.append(res_r)
+                res_ts.append(res_t)
+            for smp in range(0 if fast else S):
                 fr = slice(smp * T, (smp + 1) * T)
                 pr = slice(smp * n_pairs, (smp + 1) * n_pairs)
                 points = [[p[:, cols][None]] for p in feats[fr]]

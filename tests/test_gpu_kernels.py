@@ -492,3 +492,36 @@ def test_bn1d_over_stacked_frames_matches_float64(cuda, C, seg, train, slope):
         assert torch.equal(rm_k, rm) and torch.equal(rv_k, rv) and int(nbt) == 0
     assert rel(dx, xd.grad) < 2e-5
     assert rel(dgamma, gd.grad) < 1e-5 and rel(dbeta, bd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("n,identity", [(40000, False), (37, False), (5000, True)])
+def test_pair_transform_matches_torch_float64(cuda, n, identity):
+    """csrc/pair_transform.cu: y = x @ R(q)^T + t with the kornia-0.4.0 conversion restated in rslo_b200/utils/pose_utils.py
+    (the torch chain it replaces, `voxel_odom_net.py:671-690`), forward, R, and gradients w.r.t. q (w,x,y,z) and t;
+    x is the xyz part of 7-column rows (row-strided view)."""
+    from rslo_b200 import kernels as K
+    from rslo_b200.utils import pose_utils
+    g = torch.Generator().manual_seed(n)
+    feats = (torch.randn(n, 7, generator=g) * 20).cuda()
+    q = torch.tensor([[0.9, 0.05, -0.1, 0.3]]) * 1.7                      # not normalised on purpose
+    t = torch.tensor([[0.8, -0.2, 0.05]])
+    gy = torch.randn(n, 3, generator=g).cuda()
+    qk, tk = q.cuda().requires_grad_(True), t.cuda().requires_grad_(True)
+    y, R = K.pair_transform(feats, qk[0], tk[0], identity=identity)
+    qd, td = q.double().cuda().requires_grad_(True), t.double().cuda().requires_grad_(True)
+    if identity:
+        Rd = torch.eye(3, dtype=torch.float64, device="cuda")[None]
+        yd = feats[:, :3].double()[None] @ Rd.transpose(1, 2)
+    else:
+        Rd = pose_utils.quaternion_to_rotation_matrix(torch.roll(qd, -1, -1))
+        yd = feats[:, :3].double()[None] @ Rd.transpose(1, 2) + td[:, None, :]
+
+    def rel(a, b):
+        return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert rel(y, yd[0]) < 1e-6 and rel(R, Rd[0]) < 1e-6
+    (y * gy).sum().backward()
+    if identity:
+        assert qk.grad is None or float(qk.grad.abs().max()) == 0
+        return
+    (yd[0] * gy.double()).sum().backward()
+    assert rel(qk.grad, qd.grad) < 1e-5 and rel(tk.grad, td.grad) < 1e-5

@@ -265,3 +265,38 @@ def test_display_outputs_on_demand_equal_the_eager_ones(net):
         assert torch.equal(x, y.cpu())
     assert torch.equal(a["loss"].detach().cpu(), b["loss"].detach().cpu())
     net.zero_grad()
+
+
+def test_encoder_engine_matches_layerwise_path(net):
+    """layers/encoder_engine.py (one autograd node over the 25 sparse layers) against the layer-by-layer modules of
+    layers/sparse3d.py on the same step: same kernels in the same order -> identical outputs; gradients equal up to
+    the summation order of the weight-gradient atomics."""
+    from rslo_b200.layers import encoder_engine
+    net, vg = net
+    onet.fill_weights(net, 11)
+    net.global_step.fill_(2000)
+    net._step_host = None
+    net.train()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    pts = [torch.from_numpy(f).cuda() for f in mg.make_frames(6, 16, 600, 2)]
+    res = []
+    for use in (False, True):
+        encoder_engine.USE_ENGINE = use
+        try:
+            net.load_state_dict(sd0)
+            net.zero_grad()
+            ret = net({"points": pts, "host_outputs": False})
+            ret["loss"].sum().backward()
+        finally:
+            encoder_engine.USE_ENGINE = True
+        res.append((ret["loss"].detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None},
+                    {k: v.clone() for k, v in net.state_dict().items() if "running_" in k or "num_batches" in k}))
+    (la, ga, ba), (lb, gb, bb) = res
+    assert torch.equal(la, lb)
+    assert ga.keys() == gb.keys()
+    for k in ga:
+        scale = float(ga[k].abs().max())       # (biases ahead of a batch-statistics BatchNorm: true gradient 0, 1e-10 noise)
+        assert float((ga[k] - gb[k]).abs().max()) <= 2e-5 * scale + 1e-8, k
+    for k in ba:
+        assert torch.equal(ba[k], bb[k]), k
+    net.zero_grad()
