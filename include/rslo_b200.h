@@ -99,6 +99,16 @@ int rslo_strided_table(const int32_t* coors, int coor_stride, int n_cap, const i
 /* Several frames share one pass through the encoder: their tables are appended row-wise, row indices of
  * frame f shifted by the number of rows before it.  dst[i] = src[i] >= 0 ? src[i] + add : -1. */
 int rslo_table_concat(const int32_t* src, long long count, int add, int32_t* dst, rslo_stream_t stream);
+/* the same for nseg (source, destination) segments in one launch per RSLO_CONCAT_MAX segments (host array) */
+#define RSLO_CONCAT_MAX 64
+typedef struct {
+    const int32_t* src;
+    int32_t* dst;
+    long long count;
+    int add;
+    int reserved;
+} rslo_concat_seg_t;
+int rslo_table_concat_multi(const rslo_concat_seg_t* segs_host, int nseg, rslo_stream_t stream);
 
 /* ---- a6: sparse convolution ---------------------------------------------------------------------
  * out[o,:] = act( scale * (bias + sum_k in[nbr[o,k],:] @ W[k]) + shift )

@@ -42,6 +42,7 @@ SIGNATURES = {
     "rslo_strided_table": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                 _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rslo_table_concat": (_i, [_vp, C.c_longlong, _i, _vp, _vp]),
+    "rslo_table_concat_multi": (_i, [_vp, _i, _vp]),
     "rslo_spconv_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "rslo_spconv_transpose_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "rslo_spconv_backward_data": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -109,6 +110,10 @@ def _bind():
 
 
 _bind()
+
+
+class ConcatSeg(C.Structure):            # rslo_concat_seg_t
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("count", C.c_longlong), ("add", C.c_int), ("reserved", C.c_int)]
 
 
 class AdamChunk(C.Structure):            # rslo_adam_chunk_t

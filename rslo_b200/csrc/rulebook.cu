@@ -135,6 +135,31 @@ __global__ void k_table_concat(const int* __restrict__ src, long long count, int
     }
 }
 
+// the same for up to RSLO_CONCAT_MAX (source, destination) segments in ONE launch: the 12 tables x T frames of a step
+struct ConcatBatch {
+    rslo_concat_seg_t seg[RSLO_CONCAT_MAX];
+};
+__global__ void k_table_concat_multi(const __grid_constant__ ConcatBatch B)
+{
+    const rslo_concat_seg_t& s = B.seg[blockIdx.y];
+    const int4* __restrict__ src4 = reinterpret_cast<const int4*>(s.src);
+    int4* __restrict__ dst4 = reinterpret_cast<int4*>(s.dst);
+    const bool vec = ((((uintptr_t)s.src) | ((uintptr_t)s.dst)) & 15) == 0;
+    const long long n4 = vec ? s.count >> 2 : 0;
+    const int add = s.add;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        int4 v = __ldg(src4 + t);
+        v.x = v.x >= 0 ? v.x + add : -1; v.y = v.y >= 0 ? v.y + add : -1;
+        v.z = v.z >= 0 ? v.z + add : -1; v.w = v.w >= 0 ? v.w + add : -1;
+        dst4[t] = v;
+    }
+    for (long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < s.count;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int v = s.src[t];
+        s.dst[t] = v >= 0 ? v + add : -1;
+    }
+}
+
 // n[1] = raw number of output sites, n[0] = min(raw, cap): callers detect overflow from n[1] > cap
 __global__ void k_clamp_count(int* n, int cap)
 {
@@ -247,5 +272,25 @@ extern "C" int rslo_table_concat(const int32_t* src, long long count, int add, i
     RSLO_COUNT();
     k_table_concat<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, count, add, dst);
     RSLO_CHECK_LAUNCH("rslo_table_concat");
+    return 0;
+}
+
+extern "C" int rslo_table_concat_multi(const rslo_concat_seg_t* segs_host, int nseg, rslo_stream_t stream)
+{
+    for (int first = 0; first < nseg; first += RSLO_CONCAT_MAX) {
+        const int n = nseg - first < RSLO_CONCAT_MAX ? nseg - first : RSLO_CONCAT_MAX;
+        ConcatBatch B;
+        long long most = 1;
+        for (int i = 0; i < n; ++i) {
+            B.seg[i] = segs_host[first + i];
+            if (B.seg[i].count > most) most = B.seg[i].count;
+        }
+        int blocks = cdiv(most, 256 * 8);
+        if (blocks < 1) blocks = 1;
+        if (blocks * n > 148 * 16) blocks = cdiv(148 * 16, n);
+        RSLO_COUNT();
+        k_table_concat_multi<<<dim3(blocks, n), 256, 0, (cudaStream_t)stream>>>(B);
+        RSLO_CHECK_LAUNCH("rslo_table_concat_multi");
+    }
     return 0;
 }

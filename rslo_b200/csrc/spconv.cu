@@ -16,14 +16,26 @@
 namespace rslo {
 namespace {
 
+// Narrow outputs (COUT <= 16) would leave most lanes of a warp-per-row kernel idle in the FMA loop, so the warp is cut
+// into GROUPS = 32 / GL lane groups (GL = 16 lanes for COUT <= 16, 8 for COUT <= 8) that take DIFFERENT neighbours of the
+// row at the same time - group g the g-th, (g + GROUPS)-th, ... valid offset - and the group sums are added in a fixed
+// order at the end (deterministic).  COUT >= 32: one group, the plain k-ascending order.
+template <int COUT>
+struct FwdGroups {
+    static constexpr int GL = COUT > 16 ? 32 : (COUT > 8 ? 16 : 8);
+    static constexpr int GROUPS = 32 / GL;
+};
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 k_spconv_fwd(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap, const int* n_dev, int K,
              const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ scale,
              const float* __restrict__ shift, int act, float slope, float* __restrict__ out)
 {
-    constexpr int NA = (CIN + 31) / 32, NO = (COUT + 31) / 32;
+    constexpr int GL = FwdGroups<COUT>::GL, GROUPS = FwdGroups<COUT>::GROUPS;
+    constexpr int NA = (CIN + GL - 1) / GL, NO = (COUT + GL - 1) / GL;
     const int lane = threadIdx.x & 31;
+    const int gl = lane & (GL - 1), grp = lane / GL;
     const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= dev_count(n_dev, n_cap)) return;
     float acc[NO];
@@ -32,32 +44,45 @@ k_spconv_fwd(const float* __restrict__ in, const int* __restrict__ nbr, int n_ca
     const int mynb = lane < K ? __ldg(nbr + (size_t)row * K + lane) : -1;
     unsigned valid = __ballot_sync(0xffffffffu, mynb >= 0);
     while (valid) {
-        const int k = __ffs(valid) - 1;
-        valid &= valid - 1;
+        // this group's neighbour: the grp-th set bit of `valid` (none left: idles through the iteration with a = 0)
+        unsigned mine = valid;
+#pragma unroll
+        for (int i = 0; i < GROUPS - 1; ++i)
+            if (i < grp) mine &= mine - 1;
+        const bool has = mine != 0;
+        const int k = has ? __ffs(mine) - 1 : 0;
+#pragma unroll
+        for (int i = 0; i < GROUPS; ++i) valid &= valid - 1;               // (x & (x - 1) of 0 stays 0)
         const int j = __shfl_sync(0xffffffffu, mynb, k);
-        const float* src = in + (size_t)j * CIN;
+        const float* src = in + (size_t)(has ? j : 0) * CIN;
         float a[NA];
 #pragma unroll
-        for (int t = 0; t < NA; ++t) a[t] = (lane + 32 * t < CIN) ? __ldg(src + lane + 32 * t) : 0.f;
+        for (int t = 0; t < NA; ++t) a[t] = (has && gl + GL * t < CIN) ? __ldg(src + gl + GL * t) : 0.f;
         const float* w = W + (size_t)k * CIN * COUT;
 #pragma unroll
         for (int c = 0; c < CIN; ++c) {
-            const float av = __shfl_sync(0xffffffffu, a[c / 32], c % 32);
+            const float av = __shfl_sync(0xffffffffu, a[c / GL], (c % GL) + GL * grp);
 #pragma unroll
             for (int t = 0; t < NO; ++t)
-                if (COUT % 32 == 0 || lane + 32 * t < COUT)
-                    acc[t] = fmaf(av, __ldg(w + c * COUT + lane + 32 * t), acc[t]);
+                if (COUT % GL == 0 || gl + GL * t < COUT)
+                    acc[t] = fmaf(av, __ldg(w + c * COUT + gl + GL * t), acc[t]);
         }
     }
 #pragma unroll
-    for (int t = 0; t < NO; ++t) {
-        const int co = lane + 32 * t;
-        if (co < COUT) {
-            float v = acc[t];
-            if (bias) v += __ldg(bias + co);
-            if (scale) v = fmaf(v, __ldg(scale + co), __ldg(shift + co));
-            if (act == 1) v = v > 0.f ? v : v * slope;
-            out[(size_t)row * COUT + co] = v;
+    for (int off = GL; off < 32; off <<= 1)
+#pragma unroll
+        for (int t = 0; t < NO; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], off);
+    if (grp == 0) {
+#pragma unroll
+        for (int t = 0; t < NO; ++t) {
+            const int co = gl + GL * t;
+            if (co < COUT) {
+                float v = acc[t];
+                if (bias) v += __ldg(bias + co);
+                if (scale) v = fmaf(v, __ldg(scale + co), __ldg(shift + co));
+                if (act == 1) v = v > 0.f ? v : v * slope;
+                out[(size_t)row * COUT + co] = v;
+            }
         }
     }
 }

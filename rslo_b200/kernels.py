@@ -185,6 +185,32 @@ def strided_table(coors, n, shape, ksize, stride, pad, n_dev=None, out_cap=None)
     return SiteTable((oD, oH, oW), cells, None), out_coors, n_out_dev, nbr, nbr_inv
 
 
+def table_concat_many(jobs):
+    """jobs: list of (tables, rows, adds) as for table_concat -> list of concatenated tables, ONE launch for all of them
+    (the 12 rulebooks x T frames of a step; csrc/rulebook.cu:k_table_concat_multi)."""
+    from ._lib import ConcatSeg
+    outs, segs = [], []
+    for tables, rows, adds in jobs:
+        Kk = tables[0].shape[1]
+        total = int(sum(rows))
+        out = torch.empty((max(total, 1), Kk), dtype=torch.int32, device=tables[0].device)
+        base = out.data_ptr()
+        r0 = 0
+        for t, r, a in zip(tables, rows, adds):
+            if r > 0:
+                segs.append((_i32(t).data_ptr(), base + 4 * r0 * Kk, int(r) * Kk, int(a)))
+            r0 += r
+        outs.append(out)
+    if segs:
+        arr = (ConcatSeg * len(segs))()
+        for i, (sp, dp, cnt, add) in enumerate(segs):
+            e = arr[i]
+            e.src, e.dst, e.count, e.add = sp, dp, cnt, add
+        check(lib.rslo_table_concat_multi(arr, len(segs), stream()), "rslo_table_concat_multi")
+        _count()
+    return outs
+
+
 def table_concat(tables, rows, adds):
     """Row-wise concatenation of per-frame tables [rows_f, K] with row indices shifted by adds[f]."""
     Kk = tables[0].shape[1]

@@ -125,21 +125,25 @@ def build_tables_batched(frames, sparse_shape, pending=None):
     def level_frames(l):
         return [(offs[l][f], ns[l][f], per[f][0][l]["tab"], per[f][0][l]["idx"]) for f in range(T)]
 
-    def cat(tabs, l_rows, l_vals):
-        if T == 1:
-            return tabs[0]
-        return K.table_concat(tabs, ns[l_rows], offs[l_vals])
+    # all 12 appended tables of the step in one launch
+    jobs = [([p[1][_SUBM_KEYS[li]] for p in per], ns[li], offs[li]) for li in range(4)]
+    for li, (key, ks, st, pd) in enumerate(_GEOMS):
+        jobs.append(([p[1][key][0] for p in per], ns[li + 1], offs[li]))         # out rows -> in rows
+        jobs.append(([p[1][key][1] for p in per], ns[li], offs[li + 1]))         # in rows -> out rows
+    cats = [j[0][0] for j in jobs] if T == 1 else K.table_concat_many(jobs)
+    cats = iter(cats)
+    subm_tabs = [next(cats) for _ in range(4)]
+    strided_tabs = [(next(cats), next(cats)) for _ in _GEOMS]
 
     entries = {}
     for li in range(4):
-        nbr = cat([p[1][_SUBM_KEYS[li]] for p in per], li, li)
+        nbr = subm_tabs[li]
         e = IndexEntry("subm", nbr, nbr, tot[li], tot[li], per[0][0][li]["idx"] if T == 1 else None,
                        per[0][0][li]["shape"], per[0][0][li]["tab"] if T == 1 else None, True)
         e.seg_in = e.seg_out = ns[li]
         entries[_SUBM_KEYS[li]] = e
     for li, (key, ks, st, pd) in enumerate(_GEOMS):
-        nbr = cat([p[1][key][0] for p in per], li + 1, li)             # out rows -> in rows
-        nbr_inv = cat([p[1][key][1] for p in per], li, li + 1)         # in rows -> out rows
+        nbr, nbr_inv = strided_tabs[li]
         o0, i0 = per[0][0][li + 1], per[0][0][li]
         e = IndexEntry("strided", nbr, nbr_inv, tot[li], tot[li + 1], o0["idx"] if T == 1 else None, o0["shape"],
                        o0["tab"] if T == 1 else None, False)
