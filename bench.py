@@ -59,6 +59,11 @@ def parse_args():
 OPT = {"lr": 0.8e-4, "mom": 0.95, "beta": 0.99, "eps": 1e-8, "wd": 1e-5, "max_norm": 10.0}
 
 
+def optimizer_note(train):
+    return (f"every train step ends with clip_grad_norm {OPT['max_norm']:g} + true weight decay + Adam (lr {OPT['lr']}, "
+            f"betas ({OPT['mom']}, {OPT['beta']}), wd {OPT['wd']})") if train else None
+
+
 def workload_config(workload, pairs_per_gpu=None, max_voxels=None):
     if workload == "eval":
         return {"workload": "C2 eval fwd: 120k-pt pair (64 beams x 1875 az), voxel 0.1x0.1x0.2 m, <=40000 voxels/frame, "
@@ -185,8 +190,10 @@ def reference_arm(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": done, "warmup": w_done, "ms_per_step": 1e3 * dt / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": public_config(cfg, 1, {"note": "CPU arm: rank 0 only, one replica's batch per step; steps/warm-up "
-                                                     f"bounded by --cpu-budget-s {args.cpu_budget_s:.0f}"}),
+            "config": public_config(cfg, 1, {
+                "l2": "n/a (CPU arm)", "grad_allreduce_bytes": 0, "optimizer": optimizer_note(cfg["mode"] == "train"),
+                "note": "CPU arm: rank 0 only, one replica's batch per step; steps/warm-up bounded by "
+                        f"--cpu-budget-s {args.cpu_budget_s:.0f}"}),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -673,8 +680,7 @@ def main():
                     "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
                           f"{max(2 * ppg, 4)} distinct pairs per rank",
                     "grad_allreduce_bytes": reducer_bytes,
-                    "optimizer": ("every train step ends with clip_grad_norm 10 + true weight decay + Adam (fused, 2 launches; "
-                                  f"lr {OPT['lr']}, betas ({OPT['mom']}, {OPT['beta']}), wd {OPT['wd']})") if run_train else None}),
+                    "optimizer": optimizer_note(run_train)}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "extra": extra}
         print(json.dumps(line), flush=True)

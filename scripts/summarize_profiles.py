@@ -96,6 +96,24 @@ def reports(rnd):
                     i = hdr.index(k)
                     f.write(f"| `{k}` | {units[i]} | " + " | ".join(r[i] for r in data) + " |\n")
         print("report:", fn)
+        # DRAM traffic per launch (bench.py reads it back into roofline.traffic)
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = [float(r[ir].replace(",", "")) * scale.get(units[ir], 1.0) +
+                   float(r[iw].replace(",", "")) * scale.get(units[iw], 1.0) for r in data]
+            name = {"conv2d_wgrad_tc": "conv2d_tc_wgrad", "spconv_fwd": "spconv_forward"}.get(m.group(1), m.group(1))
+            TRAFFIC[name] = {"dram_bytes_per_launch_avg": sum(tot) / len(tot), "launches_captured": len(tot),
+                             "source": f"profiles/{rnd}_{m.group(1)}_ncu.md (ncu --set full inside bench.py --steps 1)"}
+        except ValueError:
+            pass
+    if TRAFFIC:
+        import json
+        with open(os.path.join(OUT, f"{rnd}_traffic.json"), "w") as f:
+            json.dump(TRAFFIC, f, indent=1)
+
+
+TRAFFIC = {}
 
 
 if __name__ == "__main__":
