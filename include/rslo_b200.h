@@ -374,6 +374,20 @@ int rslo_pair_transform_forward(const float* x, int ldx, int n, const float* q_w
 int rslo_pair_transform_backward(const float* grad_y, const float* x, int ldx, int n, const float* q_wxyz, float* dq_wxyz,
                                  float* dt, void* workspace, size_t workspace_bytes, rslo_stream_t stream);
 
+/* ---- f-N4: KITTI odometry sequence evaluation (csrc/kitti_eval.cu), float64 -----------------------------------
+ * rslo_odom_to_abs_pose: relative poses [n,7] (t, q = w,x,y,z) -> absolute poses [n,7] exactly as
+ * geometric.odom_to_abs_pose chains them (rslo/utils/geometric.py:376-406: abs[0] = identity, running pose starts at
+ * odoms[0], quaternion renormalised with eps 1e-6 every step); two sequences at once (either may be NULL); dist_b
+ * (may be NULL) [n] = cumulative trajectory length of sequence b (kittiOdomEval.trajectoryDistances,
+ * rslo/utils/kitti_evaluation.py:42-61).
+ * rslo_kitti_sequence_errors: kittiOdomEval.calcSequenceErrors (:95-145): for every start frame 0, step, 2 step, ...
+ * of the ground truth and the 8 segment lengths 100..800 m, row r = (start index) * 8 + (length index):
+ * err[r] = {first_frame, r_err/len, t_err/len, len, speed}, valid[r] = 0 where the reference `continue`s. */
+int rslo_odom_to_abs_pose(const double* odom_a, const double* odom_b, int n, double* abs_a, double* abs_b, double* dist_b,
+                          rslo_stream_t stream);
+int rslo_kitti_sequence_errors(const double* abs_pred, int n_pred, const double* abs_gt, int n_gt, const double* dist_gt,
+                               int step, double* err, int32_t* valid, rslo_stream_t stream);
+
 /* ---- f-N2: the optimizer step in two launches (csrc/optim.cu) --------------------------------------------
  * Replaces torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0) (train_hdf5.py:671) followed by
  * OptimWrapper.step() (rslo/torchplus/train/fastai_optim.py:181-194: p *= 1 - wd*lr on every trainable parameter,

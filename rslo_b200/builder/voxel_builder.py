@@ -1,4 +1,6 @@
 """Voxel generator builder (`rslo/builder/voxel_builder.py:36-95`)."""
+import os
+
 import numpy as np
 import torch
 
@@ -22,6 +24,13 @@ class _VoxelGenerator:
         self.block_filtering = block_filtering
         self.block_factor, self.block_size = int(block_factor), int(block_size)
         self.height_threshold = float(height_threshold)
+        # SURVEY §8b threading model: the reference calls generate() inside forked DataLoader workers
+        # (`preprocess.py:493`), where CUDA cannot be used.  pass_through=True makes generate() a copy-free
+        # packing of the raw scan into the reference's three slots - voxels [P,1,F] (one point per "voxel"),
+        # coordinates [P,3] = -1 (sentinel), num_points_per_voxel [P] = 1 - which `merge_second_batch` /
+        # `example_convert_to_torch` carry to the GPU unchanged; the network's forward recognises the layout and runs
+        # the fused voxeliser + VFE on the device (models/voxel_odom_net.py).  train_hdf5.py stays as it is.
+        self.pass_through = os.environ.get("RSLO_VOXELIZE_IN_FORWARD", "0") == "1"
 
     @property
     def grid_size(self):
@@ -39,6 +48,10 @@ class _VoxelGenerator:
                           with_table=with_table, coor_stride=3 if not with_table else 4)
 
     def generate(self, points, max_voxels=None):
+        if self.pass_through:
+            pts = np.ascontiguousarray(points, dtype=np.float32)
+            return {"voxels": pts[:, None, :], "coordinates": np.full((pts.shape[0], 3), -1, dtype=np.int32),
+                    "num_points_per_voxel": np.ones(pts.shape[0], dtype=np.int32)}
         out = self.generate_device(points, max_voxels)
         n = int(out["n_dev"].item())
         return {"voxels": out["voxels"][:n].cpu().numpy(), "coordinates": out["coordinates"][:n].cpu().numpy(),

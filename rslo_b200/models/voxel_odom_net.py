@@ -339,6 +339,13 @@ class UnVoxelOdomNetICP3(nn.Module):
     def forward(self, example):
         if self.training:
             invalidate_weight_images()      # weights move every step, possibly through .data
+        if ("voxels" in example and "points" not in example and "_prepared" not in example
+                and example["voxels"][0].dim() == 3 and example["voxels"][0].shape[1] == 1
+                and self.voxel_generator.max_num_points != 1):
+            # pass-through layout of `_VoxelGenerator.generate(pass_through=True)`: voxels [P,1,F] ARE the raw scan in
+            # scan order; voxelise on the device (bit-identical to voxelising up front, see tests)
+            example = dict(example)
+            example["points"] = [v[:, 0, :].contiguous() for v in example["voxels"]]
         if "_prepared" in example:
             prep = example["_prepared"]
             cur = torch.cuda.current_stream()

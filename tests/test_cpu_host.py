@@ -164,3 +164,16 @@ def test_bench_reference_arm_rank_nonzero_exits_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        env=dict(os.environ, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_pass_through_generator_packs_the_raw_scan_without_cuda():
+    """f-N1: generate() in pass-through mode (what a forked DataLoader worker calls) touches no GPU API"""
+    import numpy as np
+    import rslo_b200
+    _, vg = rslo_b200.build_network(testing=True, seed=7)
+    vg.pass_through = True
+    pts = np.random.default_rng(0).normal(size=(500, 7)).astype(np.float32)
+    r = vg.generate(pts, 40000)
+    assert r["voxels"].shape == (500, 1, 7) and np.array_equal(r["voxels"][:, 0], pts)
+    assert r["coordinates"].shape == (500, 3) and r["coordinates"].dtype == np.int32 and (r["coordinates"] == -1).all()
+    assert r["num_points_per_voxel"].tolist() == [1] * 500

@@ -276,3 +276,46 @@ def test_optimizer_oracle_matches_reference_live():
         oopt.adam_step(params, clipped, state, lr, mom, 0.99, 1e-8, wd=1e-2, true_wd=True)
         for a, b in zip(params, params_ref):
             assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-7)
+
+
+def _random_odoms(n, seed):
+    rng = np.random.default_rng(seed)
+    t = np.stack([rng.normal(1.0, 0.2, n), rng.normal(0, 0.03, n), rng.normal(0, 0.01, n)], 1)
+    ang = rng.normal(0, 0.02, (n, 3))
+    q = np.concatenate([np.ones((n, 1)), 0.5 * ang], 1)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return np.concatenate([t, q], 1)
+
+
+def test_kitti_eval_quaternion_matrix_matches_scipy():
+    from scipy.spatial.transform import Rotation
+    from oracle import kitti_eval as oke
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        q = rng.normal(size=4) * rng.uniform(0.5, 2.0)
+        ref = Rotation.from_quat([q[1], q[2], q[3], q[0]]).as_matrix()
+        np.testing.assert_allclose(oke.quat_to_matrix(q), ref, atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (build container only)")
+def test_kitti_eval_oracle_matches_reference_live():
+    """f-N4 pin: oracle/kitti_eval.py against the reference's own odom_to_abs_pose and kittiOdomEval (its tq_to_RT needs
+    the absent numpy-quaternion package and is handed the oracle's restatement of that one conversion)."""
+    from oracle import kitti_eval as oke
+    ref_shim.install()
+    from rslo.utils import geometric, kitti_evaluation
+    gts, preds = _random_odoms(1500, 3), _random_odoms(1500, 3)
+    preds[:, :3] += np.random.default_rng(4).normal(0, 0.02, (1500, 3))
+    a_ref, a_orc = geometric.odom_to_abs_pose(gts), oke.odom_to_abs_pose(gts)
+    np.testing.assert_allclose(a_orc, a_ref, rtol=0, atol=1e-9)
+    kitti_evaluation.tq_to_RT = oke.tq_to_RT
+    ev = kitti_evaluation.kittiOdomEval()
+    p_ref, p_orc = geometric.odom_to_abs_pose(preds), oke.odom_to_abs_pose(preds)
+    e_ref = ev.calcSequenceErrors(p_ref, a_ref)
+    e_orc = oke.calc_sequence_errors(p_orc, a_orc)
+    assert len(e_ref) == len(e_orc) > 300
+    np.testing.assert_allclose(np.asarray(e_orc), np.asarray(e_ref), rtol=1e-7, atol=1e-12)
+    s_ref = ev.computeSegmentErr(e_ref)
+    s_orc = oke.segment_errors(e_orc)
+    assert s_ref.keys() == s_orc.keys()
+    np.testing.assert_allclose(oke.segment_avg(s_orc), ev.computeSegmentAvgErr(s_ref), rtol=1e-9)

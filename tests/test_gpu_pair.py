@@ -300,3 +300,32 @@ def test_encoder_engine_matches_layerwise_path(net):
     for k in ba:
         assert torch.equal(ba[k], bb[k]), k
     net.zero_grad()
+
+
+def test_pass_through_generator_layout_is_voxelised_in_forward(net):
+    """SURVEY §8b / f-N1: with `voxel_generator.pass_through` the worker-side generate() only packs the raw scan into
+    the reference's voxels / coordinates / num_points slots (no CUDA in forked DataLoader workers); forward recognises
+    the layout, voxelises on the device and gives the same outputs as the up-front voxelisation, bit for bit."""
+    net, vg = net
+    g, frames, _ = _prep(net, "small_eval")
+    net.eval()
+    ex_ref = {"voxels": [], "num_points": [], "coordinates": [], "num_voxels": []}
+    ex_pt = {"voxels": [], "num_points": [], "coordinates": [], "num_voxels": []}
+    for f in frames:
+        for ex, pt in ((ex_ref, False), (ex_pt, True)):
+            vg.pass_through = pt
+            try:
+                r = vg.generate(f, 40000)
+            finally:
+                vg.pass_through = False
+            n = len(r["coordinates"])
+            ex["voxels"].append(torch.from_numpy(r["voxels"]).cuda())
+            ex["num_points"].append(torch.from_numpy(r["num_points_per_voxel"]).cuda())
+            ex["coordinates"].append(torch.from_numpy(np.concatenate([np.zeros((n, 1), np.int32), r["coordinates"]], 1)).cuda())
+            ex["num_voxels"].append(torch.tensor([[n]], dtype=torch.int64))
+    assert ex_pt["voxels"][0].shape[1:] == (1, 7) and int(ex_pt["coordinates"][0][:, 1:].max()) == -1
+    with torch.no_grad():
+        a = net(ex_ref)
+        b = net(ex_pt)
+    for k in ("translation_preds", "rotation_preds", "tq_map_g"):
+        assert torch.equal(a[k], b[k]), k
