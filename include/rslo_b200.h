@@ -388,6 +388,16 @@ int rslo_odom_to_abs_pose(const double* odom_a, const double* odom_b, int n, dou
 int rslo_kitti_sequence_errors(const double* abs_pred, int n_pred, const double* abs_gt, int n_gt, const double* dist_gt,
                                int step, double* err, int32_t* valid, rslo_stream_t stream);
 
+/* ---- f-N3: point-cloud normal estimation (csrc/normals.cu) -------------------------------------------------------
+ * Replaces estimate_normal() of script/create_hdf5.py:130-147 (open3d estimate_normals with
+ * KDTreeSearchParamHybrid(radius, max_nn) + orient_normals_towards_camera_location): xyz rows are ld floats apart;
+ * neighbours = the <= max_nn (<= 32) nearest points within radius, the point itself included; >= 3 neighbours: unit
+ * eigenvector of the smallest eigenvalue of their covariance, else (0,0,1); every normal flipped to face camera_host[3].
+ * normals [n,3].  workspace: rslo_estimate_normals_workspace_bytes(n). */
+size_t rslo_estimate_normals_workspace_bytes(int n);
+int rslo_estimate_normals(const float* xyz, int ld, int n, float radius, int max_nn, const float* camera_host,
+                          float* normals, void* workspace, size_t workspace_bytes, rslo_stream_t stream);
+
 /* ---- f-N2: the optimizer step in two launches (csrc/optim.cu) --------------------------------------------
  * Replaces torch.nn.utils.clip_grad_norm_(net.parameters(), 10.0) (train_hdf5.py:671) followed by
  * OptimWrapper.step() (rslo/torchplus/train/fastai_optim.py:181-194: p *= 1 - wd*lr on every trainable parameter,

@@ -91,6 +91,8 @@ SIGNATURES = {
     "rslo_pair_transform_backward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rslo_odom_to_abs_pose": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rslo_kitti_sequence_errors": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "rslo_estimate_normals_workspace_bytes": (_sz, [_i]),
+    "rslo_estimate_normals": (_i, [_vp, _i, _i, _f, _i, C.POINTER(_f), _vp, _vp, _sz, _vp]),
     "rslo_grad_norm_workspace_bytes": (_sz, []),
     "rslo_grad_sumsq": (_i, [_vp, _sz, _vp, _vp, _sz, _vp]),
     "rslo_adam_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _vp]),
