@@ -11,8 +11,9 @@
 // bias + LeakyReLU and writes the rows.
 //
 // FP32 fidelity (the path's parity bound is 1e-4 relative, which plain TF32 misses): split-TF32.
-// Each operand is split as x = hi + lo with hi = RN_tf32(x) and lo = x - hi (exact in fp32, |lo| <=
-// 2^-12 |x|; the tensor core keeps lo's top 11 bits, so the pair represents x to ~2^-22 relative), and
+// Each operand is split as x ~ hi + lo with hi = RN_tf32(x) and lo = RN_tf32(x - hi) (|lo| <= 2^-12 |x|; rounding
+// lo to TF32 here, to nearest, instead of letting the tensor core truncate its low bits halves the representation
+// error and removes its bias: the pair represents x to ~2^-23 relative), and
 // the three products lo*hi + hi*lo + hi*hi are accumulated (lo*lo is below 2^-24 relative).  The splits
 // are made while staging (A) / in the weight prep kernel (B), so the tensor core only ever sees
 // operands that are already TF32-exact (no dependence on how the hardware would round).

@@ -523,7 +523,7 @@ def _conv_ws():
 
 
 def conv2d_split(x_nhwc, out=None):
-    """x [B,H,W,C] f32 contiguous -> split pair [2,B,H,W,C] (hi = RN_tf32(x), lo = x - hi)."""
+    """x [B,H,W,C] f32 contiguous -> split pair [2,B,H,W,C] (hi = RN_tf32(x), lo = RN_tf32(x - hi))."""
     x = _f32(x_nhwc)
     if out is None:
         out = torch.empty((2,) + tuple(x.shape), dtype=torch.float32, device=x.device)

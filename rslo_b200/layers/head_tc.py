@@ -5,7 +5,7 @@ layer lists, `custom_resnet_spc.py:224-298` BasicBlock, `layers/MaskConv.py:53-6
 SyncBN/ReLU): every convolution is the TMA-staged split-TF32 tcgen05 implicit GEMM of csrc/conv2d_tc.cu (forward,
 data gradient, weight gradient), everything between two convolutions is one fused streaming kernel of
 csrc/head_ops.cu.  Activations stay NHWC and are handed from layer to layer as the split pair the convolutions read
-(hi = RN_tf32(x), lo = x - hi), so there is no layout conversion, no separate BatchNorm-statistics pass (the
+(hi = RN_tf32(x), lo = RN_tf32(x - hi)), so there is no layout conversion, no separate BatchNorm-statistics pass (the
 convolution epilogue accumulates them) and no separate operand-split pass anywhere in the trunk.
 
 The engine owns no parameters: it reads the head module's `nn.Conv2d` / `nn.BatchNorm2d` parameters and buffers
