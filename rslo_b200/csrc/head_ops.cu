@@ -426,11 +426,12 @@ __global__ void k_multi_wgrad_finish(const rslo_wgrad_finish_t* __restrict__ tab
 
 static int pick_chunk(int HW, int c4n, int B)
 {
-    // ~2048 float4 items per block, at least ~2 blocks per SM over the whole launch when the tensor allows
+    // ~512 float4 items per block (2 per thread: the passes are latency-bound streaming loops, r02e_head_bn_ncu.md showed
+    // 12 % warps active at 2048), at least ~4 blocks per SM over the whole launch when the tensor allows
     long long items = (long long)HW * c4n;
-    int chunks = (int)((items + 2047) / 2048);
-    const int want = (296 + B - 1) / B;
-    if (chunks < want && items >= 1024LL * want) chunks = want;
+    int chunks = (int)((items + 511) / 512);
+    const int want = (592 + B - 1) / B;
+    if (chunks < want && items >= 256LL * want) chunks = want;
     if (chunks < 1) chunks = 1;
     int chunk = (HW + chunks - 1) / chunks;
     if (chunk < 1) chunk = 1;
