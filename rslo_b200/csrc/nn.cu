@@ -105,10 +105,15 @@ __global__ void k_nn_fill(const float* __restrict__ t, int m, const int* __restr
     sorted[pos] = make_float4(t[i * 3], t[i * 3 + 1], t[i * 3 + 2], __int_as_float(i));
 }
 
-__device__ __forceinline__ void scan_cell(const float4* __restrict__ sorted, int s, int e, float qx, float qy,
+// NN_TPQ lanes share one query: each takes every NN_TPQ-th target of a cell span, the group's best (distance, then
+// lowest index - an order-independent minimum, so the result is bit-identical to the one-thread walk) is combined
+// after every ring.  40000 queries alone are 8 warps per SM; the lane groups give the walk 8x the parallelism.
+constexpr int NN_TPQ = 8;
+
+__device__ __forceinline__ void scan_cell(const float4* __restrict__ sorted, int s, int e, int sub, float qx, float qy,
                                           float qz, float& best, int& besti)
 {
-    for (int p = s; p < e; ++p) {
+    for (int p = s + sub; p < e; p += NN_TPQ) {
         float4 t = __ldg(sorted + p);
         float d = sqdist(qx, qy, qz, t.x, t.y, t.z);
         int ti = __float_as_int(t.w);
@@ -121,8 +126,10 @@ k_nn_query(const float* __restrict__ q, int n, const NNGrid* gp, const int* __re
            const float4* __restrict__ sorted, float* __restrict__ dist, int* __restrict__ idx,
            int* __restrict__ fallback, NNGrid* gw)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) / NN_TPQ);
+    if (i >= n) return;                                   // whole lane groups leave together (n is per group)
+    const int sub = threadIdx.x & (NN_TPQ - 1);
+    const unsigned gmask = ((1u << NN_TPQ) - 1u) << ((threadIdx.x & 31) & ~(NN_TPQ - 1));
     const NNGrid g = *gp;
     const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
     const int cx = cell_of(qx, g.x0, g.inv_h, g.nx), cy = cell_of(qy, g.y0, g.inv_h, g.ny);
@@ -134,28 +141,38 @@ k_nn_query(const float* __restrict__ q, int n, const NNGrid* gp, const int* __re
         const int xl = cx - r, xh = cx + r, yl = cy - r, yh = cy + r;
         if (r == 0) {
             int c = cy * g.nx + cx;
-            scan_cell(sorted, __ldg(start + c), __ldg(start + c + 1), qx, qy, qz, best, besti);
+            scan_cell(sorted, __ldg(start + c), __ldg(start + c + 1), sub, qx, qy, qz, best, besti);
         } else {
             // top and bottom rows of the ring: contiguous cell ranges -> one [start,end) span each
             const int xa = max(xl, 0), xb = min(xh, g.nx - 1);
             if (yl >= 0) {
                 int c = yl * g.nx;
-                scan_cell(sorted, __ldg(start + c + xa), __ldg(start + c + xb + 1), qx, qy, qz, best, besti);
+                scan_cell(sorted, __ldg(start + c + xa), __ldg(start + c + xb + 1), sub, qx, qy, qz, best, besti);
             }
             if (yh < g.ny) {
                 int c = yh * g.nx;
-                scan_cell(sorted, __ldg(start + c + xa), __ldg(start + c + xb + 1), qx, qy, qz, best, besti);
+                scan_cell(sorted, __ldg(start + c + xa), __ldg(start + c + xb + 1), sub, qx, qy, qz, best, besti);
             }
             const int ya = max(yl + 1, 0), yb = min(yh - 1, g.ny - 1);
             for (int y = ya; y <= yb; ++y) {
                 if (xl >= 0) {
                     int c = y * g.nx + xl;
-                    scan_cell(sorted, __ldg(start + c), __ldg(start + c + 1), qx, qy, qz, best, besti);
+                    scan_cell(sorted, __ldg(start + c), __ldg(start + c + 1), sub, qx, qy, qz, best, besti);
                 }
                 if (xh < g.nx) {
                     int c = y * g.nx + xh;
-                    scan_cell(sorted, __ldg(start + c), __ldg(start + c + 1), qx, qy, qz, best, besti);
+                    scan_cell(sorted, __ldg(start + c), __ldg(start + c + 1), sub, qx, qy, qz, best, besti);
                 }
+            }
+        }
+        // the group's best so far
+#pragma unroll
+        for (int o = NN_TPQ / 2; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(gmask, best, o);
+            const int oi = __shfl_xor_sync(gmask, besti, o);
+            if (ob < best || (ob == best && oi < besti)) {
+                best = ob;
+                besti = oi;
             }
         }
         // lower bound on the distance to anything not yet explored
@@ -171,6 +188,7 @@ k_nn_query(const float* __restrict__ q, int n, const NNGrid* gp, const int* __re
             if (bound > 0.f && best < bound * bound * (1.f - 1e-4f)) done = true;
         }
     }
+    if (sub != 0) return;
     if (done) {
         dist[i] = best;
         idx[i] = besti;
@@ -301,7 +319,7 @@ extern "C" int rslo_nn_exact(const float* query, int n, const float* target, int
     RSLO_COUNT();
     k_nn_fill<<<cdiv(m, 256), 256, 0, st>>>(target, m, cell_of_pt, start, fill, sorted);
     RSLO_COUNT();
-    k_nn_query<<<cdiv(n, 128), 128, 0, st>>>(query, n, g, start, sorted, dist, idx, fallback, g);
+    k_nn_query<<<cdiv((long long)n * NN_TPQ, 128), 128, 0, st>>>(query, n, g, start, sorted, dist, idx, fallback, g);
     RSLO_COUNT();
     k_nn_fallback<<<148 * 2, 256, 0, st>>>(query, target, m, g, fallback, dist, idx);
     RSLO_CHECK_LAUNCH("rslo_nn_exact");
