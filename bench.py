@@ -191,7 +191,7 @@ def reference_arm(args, cfg):
             "steps": done, "warmup": w_done, "ms_per_step": 1e3 * dt / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": public_config(cfg, 1, {
-                "l2": "n/a (CPU arm)", "grad_allreduce_bytes": 0, "optimizer": optimizer_note(cfg["mode"] == "train"),
+                "l2": "n/a (CPU arm)", "steps_in_flight": "n/a (CPU arm)", "grad_allreduce_bytes": 0, "optimizer": optimizer_note(cfg["mode"] == "train"),
                 "note": "CPU arm: rank 0 only, one replica's batch per step; steps/warm-up bounded by "
                         f"--cpu-budget-s {args.cpu_budget_s:.0f}"}),
             "cpu_baseline": cb,
@@ -213,7 +213,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -293,6 +293,7 @@ class Runner:
     step function through the public API (net.prepare on a side stream one step ahead, net(example), backward,
     flat gradient all-reduce) and the timed loop."""
     PREFETCH_DEPTH = 1
+    MAX_STEPS_IN_FLIGHT = 2           # the host enqueues at most this many steps ahead of the device
 
     def __init__(self, cfg, dev, rank, world):
         import torch
@@ -328,6 +329,10 @@ class Runner:
         if os.environ.get("RSLO_BENCH_PREFETCH_THREAD", "0") != "0":     # measured: GIL contention outweighs the overlap
             from rslo_b200.data.prefetch import PreparedPrefetcher
             self.prefetcher = PreparedPrefetcher(net, dev)
+        from rslo_b200.utils.memory import InflightLimiter
+        self.limiter = InflightLimiter(self.MAX_STEPS_IN_FLIGHT)
+        self.result_slots = [[None, None], [None, None]]     # pinned result buffer + copy-done event, double-buffered
+        self.last_result = None
         self.host_s = 0.0
         self.host_phase = {"forward": 0.0, "backward": 0.0, "prepare": 0.0, "reduce+optimizer": 0.0, "steps": 0}
 
@@ -386,9 +391,34 @@ class Runner:
             ph["reduce+optimizer"] += time.perf_counter() - t4
         ph["steps"] += 1
         if from_host:
-            r = res.cpu()                                                  # D2H of the step's result
-            self.d2h_bytes += r.numel() * 4
+            # D2H of the step's result, every step: asynchronous copy into pinned memory, read by the host one step
+            # later (while the next step runs), as the scans are copied one step early
+            slot = self.result_slots[i % 2]
+            if slot[0] is None or slot[0].numel() != res.numel():
+                slot[0] = torch.empty(res.numel(), dtype=res.dtype).pin_memory()
+            self.read_result(1 - i % 2)
+            slot[0].copy_(res, non_blocking=True)
+            slot[1] = torch.cuda.Event()
+            slot[1].record()
+            self.d2h_bytes += res.numel() * 4
+        self.limiter.tick()
         return res
+
+    def read_result(self, k):
+        """host read of the result copied by an earlier step (waits for its copy)"""
+        buf, ev = self.result_slots[k]
+        if ev is not None:
+            ev.synchronize()
+            self.last_result = buf.tolist()
+            self.result_slots[k][1] = None
+
+    def presize_pools(self):
+        """after the warm-up steps: give every stream's allocator pool its head-room once, so no timed step calls
+        cudaMalloc (rslo_b200/utils/memory.py: a cudaMalloc next to a polling nvidia-smi stalls the step 10-100 ms)"""
+        from rslo_b200.utils.memory import presize_stream_pools
+        torch = self.torch
+        presize_stream_pools([torch.cuda.current_stream(self.dev), self.net.__dict__.get("_prep_stream"),
+                              getattr(self.reducer, "_comm", None)])
 
     def timed(self, nsteps, from_host, first):
         """-> (total ms of exactly nsteps steps, max over ranks; per-step ms on this rank)"""
@@ -407,6 +437,8 @@ class Runner:
             self.step(first + i, from_host)
             evs[i + 1].record()
         self.host_s = time.time() - t_host                                 # time the training thread needed to ENQUEUE
+        for k in (0, 1):                                                   # the last steps' results reach the host
+            self.read_result(k)
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
@@ -428,6 +460,7 @@ class Runner:
         """pairs/s of this workload, device-resident inputs (used for the extras)"""
         for i in range(warmup):
             self.step(i, False)
+        self.presize_pools()
         ms, per = self.timed(steps, False, warmup)
         self.close()
         per.sort()
@@ -586,6 +619,7 @@ def main():
     W = max(args.warmup, 3)
     for i in range(W):
         run.step(i, False)
+    run.presize_pools()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -605,7 +639,7 @@ def main():
     value = world * ppg * args.steps / (ms / 1e3)
 
     # e2e: host buffers -> net.prepare / net(example) -> host result
-    for i in range(3):
+    for i in range(max(3, W // 2)):
         run.step(i, True)
     run.h2d_bytes = run.d2h_bytes = 0
     ms_e2e, per_e2e = run.timed(args.steps, True, W)
@@ -613,6 +647,8 @@ def main():
            "h2d_bytes_per_step": run.h2d_bytes // (args.steps + run.PREFETCH_DEPTH),
            "d2h_bytes_per_step": run.d2h_bytes // args.steps,
            "ms_per_step": ms_e2e / args.steps, "ms_per_step_median": median(per_e2e),
+           "result_read": "loss copied D2H into pinned memory every step, read by the host one step later; all K "
+                          "results are on the host when the timed region ends",
            "host_phase_ms_per_step": {k: 1e3 * v / max(run.host_phase["steps"], 1) for k, v in run.host_phase.items()
                                       if k != "steps"}}
 
@@ -679,6 +715,7 @@ def main():
                 "config": public_config(cfg, world, {
                     "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
                           f"{max(2 * ppg, 4)} distinct pairs per rank",
+                    "steps_in_flight": f"host at most {Runner.MAX_STEPS_IN_FLIGHT} steps ahead of the device (event wait)",
                     "grad_allreduce_bytes": reducer_bytes,
                     "optimizer": optimizer_note(run_train)}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
