@@ -22,6 +22,15 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     run = bench.Runner(cfg, dev, 0, 1)
+    if "reuse" in variants:          # upper bound of what removing the preparation-stream work could buy
+        cache = {}
+        orig = run.prepared_step
+        def cached(i, fh):
+            k = i % run.pool_n
+            if k not in cache:
+                cache[k] = orig(i, fh)
+            return cache[k]
+        run.prepared_step = cached
     for i in range(20):
         run.step(i, from_host)
     if "presize" in variants:

@@ -52,7 +52,8 @@ def launches(rnd):
     own = sum(a[1] for k, a in agg.items() if k.startswith("k_"))
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
     with open(os.path.join(OUT, f"{rnd}_launches_bench.md"), "w") as f:
-        f.write(f"# ncu launch list — one timed step of `bench.py --steps 1 --warmup 3 --pairs-per-gpu 1` ({rnd})\n\n")
+        cmd = "bench.py --steps 1 --warmup 3 --pairs-per-gpu 1" if rnd.startswith("r01") else "bench.py --steps 1 --warmup 3 (the bench's train step: 2 pairs per GPU)"
+        f.write(f"# ncu launch list — one timed step of `{cmd}` ({rnd})\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off` (cold-cache, "
                 "serialised: compare SHARES, not absolutes).\n\n")
         f.write(f"launches: {sum(a[0] for a in agg.values())}, summed kernel time: {tot / 1e3:.2f} ms; "
