@@ -136,7 +136,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t base = smem_u32(smem);
             int st = 0;
             if constexpr (HALO) {
@@ -174,7 +174,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(NT);
             uint32_t acc = 0;
             if constexpr (HALO) {
@@ -741,7 +741,7 @@ k_conv2d_wgrad_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int per_img = P.tiles_h * P.tiles_w;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t sA_u = smem_u32(sA), sG_u = smem_u32(sG);
             int item = 0;
             for (int stp = step0; stp < step1; ++stp) {
@@ -780,7 +780,7 @@ k_conv2d_wgrad_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32_mn(NT);
             constexpr uint32_t LBO = WG_CHUNK_BYTES;
             int item = 0;

@@ -34,8 +34,15 @@ namespace {
 using namespace tc;
 
 constexpr int TC_ROWS = 128;
-constexpr int TC_PRODUCERS = 128;          // warps 0..3: gather
-constexpr int TC_THREADS = 288;            // + warp 4: TMEM owner and MMA issuer; warps 5..8: drain + epilogue
+// The gather producers pace this kernel (profiles/r02_tc_kernel_diagnostics.md: never parked, 17 % issuing, the rest
+// dependency latency of one warp per scheduler), so a CTA carries 8 producer warps (16 rows each) and, to stay at two
+// CTAs per SM within the register file, 8 drain warps that own half of the accumulator columns each.
+constexpr int TC_PRODUCER_WARPS = 8;       // warps 0..7: gather
+constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
+constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;        // warp 8: TMEM owner and MMA issuer
+constexpr int TC_DRAIN_WARPS = 8;          // warps 9..16: drain + epilogue (two per TMEM lane quarter)
+constexpr int TC_DRAINERS = TC_DRAIN_WARPS * 32;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_DRAIN_WARPS) * 32;     // 544
 
 // ---- weight prep: W [K,Cin,Cout] -> per-offset images {B_hi, B_lo}, B is [NDIM x KDIM] K-major ----
 //   forward      (transpose = 0): NDIM = Cout, KDIM = Cin,  B(n, kk) = W[k][kk][n]
@@ -76,8 +83,8 @@ struct TcSmem {
     static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + NBR_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
 
-// Named barrier among the 128 drain threads only (barrier 0 is __syncthreads).
-__device__ __forceinline__ void drain_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Named barrier among the drain threads only (barrier 0 is __syncthreads).
+__device__ __forceinline__ void drain_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_DRAINERS) : "memory"); }
 
 // grid = (row tiles, split).  CTA (tile, sidx) handles every split-th active kernel offset of its tile;
 // with split > 1 each CTA parks its partial sums in `scratch` and the last one to finish adds them in
@@ -121,12 +128,12 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         }
         mbar_init(tfull_bar + 0, 1);
         mbar_init(tfull_bar + 1, 1);
-        mbar_init(tempty_bar + 0, 128);
-        mbar_init(tempty_bar + 1, 128);
+        mbar_init(tempty_bar + 0, TC_DRAINERS);
+        mbar_init(tempty_bar + 1, TC_DRAINERS);
         *s_mask = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(TCOLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -134,6 +141,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     __syncthreads();
     // neighbour tile -> smem, and the set of offsets this tile uses
     unsigned my_mask = 0;
+#pragma unroll 4
     for (int i = tid; i < TC_ROWS * K; i += TC_THREADS) {
         const int r = i / K, k = i - r * K;
         const int o = row0 + r;
@@ -167,24 +175,25 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     }
     __syncthreads();
 
-    if (warp < 4) {
+    if (warp < TC_PRODUCER_WARPS) {
         // ================= producers: gather neighbour rows, split to TF32 hi/lo, swizzled store =================
         constexpr int CHUNKS = TC_KS / 4;                // 16-byte chunks per staged row segment (128 B)
         constexpr int ROWS_PER_LD = 32 / CHUNKS;         // 4 rows per warp-wide load
-        constexpr int NLD = 32 / ROWS_PER_LD;            // 8 loads per warp per step, all in flight together
+        constexpr int ROWS_PER_WARP = TC_ROWS / TC_PRODUCER_WARPS;       // 16
+        constexpr int NLD = ROWS_PER_WARP / ROWS_PER_LD; // 4 loads per thread per step, all in flight together
         const int sub = lane / CHUNKS, c = lane % CHUNKS;
         const uint32_t smem_base = smem_u32(smem);
         // per-thread swizzled store offsets of its NLD row segments (same for every step)
         uint32_t soff[NLD];
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) soff[j] = sw128_offset(warp * 32 + j * ROWS_PER_LD + sub, c * 4, TC_ROWS);
+        for (int j = 0; j < NLD; ++j) soff[j] = sw128_offset(warp * ROWS_PER_WARP + j * ROWS_PER_LD + sub, c * 4, TC_ROWS);
         int nsteps = __popc(mask) * NSUB;
 
         // gather of step st: NLD independent 16-byte loads (zeros for rows without this neighbour)
         auto gather = [&](int k, int h, float4(&v)[NLD]) {
 #pragma unroll
             for (int j = 0; j < NLD; ++j) {
-                const int r = warp * 32 + j * ROWS_PER_LD + sub;
+                const int r = warp * ROWS_PER_WARP + j * ROWS_PER_LD + sub;
                 const int src = s_nbr[r * K + k];
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #if TC_DIAG != 3
@@ -199,9 +208,9 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             mbar_wait(empty_bar + s, ((st / TC_STAGES) & 1) ^ 1);
             const uint32_t stage = smem_base + s * S::STAGE_BYTES;
 #if TC_DIAG == 1
-            if (tid == 0 && st < TC_STAGES) {
+            if (warp == 0 && st < TC_STAGES && elect_one()) {
 #else
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {      // one lane, uniform operands for the bulk copy
 #endif
                 mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
                 bulk_copy_g2s(smem + s * S::STAGE_BYTES + 2 * S::A_BYTES,
@@ -233,9 +242,12 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             if (st + 2 < nsteps) gather(kof(st + 2), (st + 2) % NSUB, va);
             publish(st + 1, kof(st + 1), (st + 1) % NSUB, vb);
         }
-    } else if (warp == 4) {
+    } else if (warp == TC_MMA_WARP) {
         // ================= MMA issuer (one elected lane) =================
-        if (lane == 0) {
+        // `elect_one()` instead of `lane == 0`: the region is single-threaded by construction, so the compiler keeps the
+        // tcgen05 operands in uniform registers; under `lane == 0` every tcgen05.mma sat inside a generated broadcast
+        // loop (ELECT / R2UR.BROADCAST / BRA.U.ANY).
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(NDIM);
             unsigned m = mask;
             for (int it = 0; m; ++it) {
@@ -272,29 +284,31 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         }
         __syncwarp();
     } else {
-        // ================= drain + epilogue warps (one output row per thread) =================
+        // ================= drain + epilogue warps (one output row x half of the channels per thread) ==============
         // The tensor core's accumulator adds are not round-to-nearest; only the 4*KDIM/8 MMAs of ONE
         // offset accumulate in TMEM, the sum over offsets is carried here in FP32 registers (RN adds).
-        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access (hardware: warp % 4)
+        const int half = (warp - TC_MMA_WARP - 1) >> 2;   // warps 9..12 take the low columns, 13..16 the high ones
+        constexpr int HC = NDIM / 2;                      // accumulator columns per thread
         const int r = q * 32 + lane;
         const int o = row0 + r;
-        float acc[NDIM];
+        float acc[HC];
 #pragma unroll
-        for (int i = 0; i < NDIM; ++i) acc[i] = 0.f;
+        for (int i = 0; i < HC; ++i) acc[i] = 0.f;
         unsigned m = mask;
         for (int it = 0; m; ++it) {
             m &= m - 1;
             const int buf = it & 1;
             mbar_wait(tfull_bar + buf, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NDIM;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NDIM + half * HC;
 #if TC_DIAG != 5
 #pragma unroll
-            for (int cb = 0; cb < NDIM; cb += 16) {
-                float v[16];
-                tmem_ld16(taddr + cb, v);
+            for (int cb = 0; cb < HC; cb += 8) {
+                float v[8];
+                tmem_ld8(taddr + cb, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[cb + i] += v[i];
+                for (int i = 0; i < 8; ++i) acc[cb + i] += v[i];
             }
 #endif
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -302,23 +316,23 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         }
         bool finish = true;
         if (split > 1) {
-            float4* mine = reinterpret_cast<float4*>(scratch + ((size_t)(wtile * split + sidx) * TC_ROWS + r) * NDIM);
+            float4* mine = reinterpret_cast<float4*>(scratch + ((size_t)(wtile * split + sidx) * TC_ROWS + r) * NDIM + half * HC);
 #pragma unroll
-            for (int i = 0; i < NDIM; i += 4) mine[i / 4] = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            for (int i = 0; i < HC; i += 4) mine[i / 4] = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
             __threadfence();
             drain_sync();
-            if (warp == 5 && lane == 0) *s_last = atomicAdd(tile_counter + wtile, 1) == split - 1;
+            if (warp == TC_MMA_WARP + 1 && lane == 0) *s_last = atomicAdd(tile_counter + wtile, 1) == split - 1;
             drain_sync();
             finish = *s_last != 0;
             if (finish) {
                 __threadfence();
 #pragma unroll
-                for (int i = 0; i < NDIM; ++i) acc[i] = 0.f;
+                for (int i = 0; i < HC; ++i) acc[i] = 0.f;
                 for (int sp = 0; sp < split; ++sp) {           // fixed order: deterministic sum
                     const float4* p = reinterpret_cast<const float4*>(
-                        scratch + ((size_t)(wtile * split + sp) * TC_ROWS + r) * NDIM);
+                        scratch + ((size_t)(wtile * split + sp) * TC_ROWS + r) * NDIM + half * HC);
 #pragma unroll
-                    for (int i = 0; i < NDIM; i += 4) {
+                    for (int i = 0; i < HC; i += 4) {
                         const float4 t = __ldcg(p + i / 4);
                         acc[i] += t.x; acc[i + 1] += t.y; acc[i + 2] += t.z; acc[i + 3] += t.w;
                     }
@@ -326,12 +340,12 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             }
         }
         if (finish && o < n) {
-            float4* dst = reinterpret_cast<float4*>(out + (size_t)o * n_total + ntile * NDIM);
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)o * n_total + ntile * NDIM + half * HC);
 #pragma unroll
-            for (int i = 0; i < NDIM; i += 4) {
+            for (int i = 0; i < HC; i += 4) {
                 float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
                 if (bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + ntile * NDIM + i));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + ntile * NDIM + half * HC + i));
                     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                 }
                 if (act == 1) {
@@ -346,7 +360,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
 }

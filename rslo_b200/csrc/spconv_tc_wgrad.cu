@@ -179,7 +179,7 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
         }
     } else if (warp == WG_PRODUCER_WARPS) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {        // single-thread region by construction: operands stay in uniform registers
             constexpr uint32_t idesc = umma_idesc_tf32_mn(COUT);
             constexpr uint32_t LBO = WG_STEP * 128;                  // bytes between 32-channel blocks
             int item = 0;
