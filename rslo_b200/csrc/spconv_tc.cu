@@ -119,7 +119,8 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     const int wtile = blockIdx.x * gridDim.z + ntile;          // work tile id (rows x channel slice)
     bimg += (size_t)ntile * K * NSUB * (2 * S::B_BYTES / 4);
     if (row0 >= n) return;                    // uniform per CTA (all splits of the tile agree)
-    constexpr int TCOLS = 2 * NDIM;           // two accumulator buffers (32, 64 or 128 columns: powers of two)
+    // two accumulator buffers of 2 * NDIM columns each: [A_hi B_hi + A_lo B_hi | A_hi B_lo] (64, 128 or 256 columns)
+    constexpr int TCOLS = 4 * NDIM;
 
     if (tid == 0) {
         for (int i = 0; i < TC_STAGES; ++i) {
@@ -248,13 +249,16 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         // tcgen05 operands in uniform registers; under `lane == 0` every tcgen05.mma sat inside a generated broadcast
         // loop (ELECT / R2UR.BROADCAST / BRA.U.ANY).
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_tf32(NDIM);
+            // The image holds {B_hi, B_lo} of a step back to back, which IS one [2 NDIM x 32] K-major tile: A_hi meets
+            // both in ONE MMA of N = 2 NDIM (columns [0, NDIM) = hi*hi, [NDIM, 2 NDIM) = hi*lo), A_lo * B_hi adds into the
+            // first half.  Two shared-memory passes over the gathered operand per K block instead of three.
+            constexpr uint32_t idesc = umma_idesc_tf32(NDIM), idesc2 = umma_idesc_tf32(2 * NDIM);
             unsigned m = mask;
             for (int it = 0; m; ++it) {
                 m &= m - 1;
                 const int buf = it & 1;
                 mbar_wait(tempty_bar + buf, ((it >> 1) & 1) ^ 1);     // accumulator buffer drained
-                const uint32_t d = tmem_base + buf * NDIM;
+                const uint32_t d = tmem_base + buf * 2 * NDIM;
                 uint32_t acc = 0;                                     // each offset starts a fresh accumulation
 #pragma unroll
                 for (int h = 0; h < NSUB; ++h) {
@@ -263,20 +267,17 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
                     const uint32_t a_lo = a_hi + S::A_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
-                    const uint32_t b_lo = b_hi + S::B_BYTES;
-#pragma unroll
-                    for (int part = 0; part < 3; ++part) {            // lo*hi, hi*lo, hi*hi (lo*lo < 2^-24 relative)
-                        const uint32_t a = part == 0 ? a_lo : a_hi;
-                        const uint32_t b = part == 1 ? b_lo : b_hi;
-#pragma unroll
-                        for (int kk = 0; kk < TC_KS / 8; ++kk) {
+                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES;      // B_lo follows at + S::B_BYTES
 #if TC_DIAG != 4
-                            umma_tf32(d, umma_desc_k_sw128(a + kk * 32), umma_desc_k_sw128(b + kk * 32), idesc, acc);
-#endif
-                            acc = 1;
-                        }
+#pragma unroll
+                    for (int kk = 0; kk < TC_KS / 8; ++kk) {          // hi*hi | hi*lo   (lo*lo < 2^-24 relative)
+                        umma_tf32(d, umma_desc_k_sw128(a_hi + kk * 32), umma_desc_k_sw128(b_hi + kk * 32), idesc2, acc);
+                        acc = 1;
                     }
+#pragma unroll
+                    for (int kk = 0; kk < TC_KS / 8; ++kk)            // lo*hi
+                        umma_tf32(d, umma_desc_k_sw128(a_lo + kk * 32), umma_desc_k_sw128(b_hi + kk * 32), idesc, 1u);
+#endif
                     umma_commit(empty_bar + s);        // stage reusable once these MMAs retire
                 }
                 umma_commit(tfull_bar + buf);          // this offset's partial product is complete
@@ -301,14 +302,14 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             const int buf = it & 1;
             mbar_wait(tfull_bar + buf, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NDIM + half * HC;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * NDIM + half * HC;
 #if TC_DIAG != 5
 #pragma unroll
             for (int cb = 0; cb < HC; cb += 8) {
-                float v[8];
-                tmem_ld8(taddr + cb, v);
+                float v[8], w[8];
+                tmem_ld8x2(taddr + cb, taddr + NDIM + cb, v, w);      // (hi*hi + lo*hi) and hi*lo of the same outputs
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[cb + i] += v[i];
+                for (int i = 0; i < 8; ++i) acc[cb + i] += v[i] + w[i];
             }
 #endif
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

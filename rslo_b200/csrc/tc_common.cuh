@@ -114,6 +114,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v)
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 8-column loads in flight together (one wait)
+__device__ __forceinline__ void tmem_ld8x2(uint32_t ta, uint32_t tb, float* v, float* w)
+{
+    uint32_t r[8], q[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(ta));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+                 : "r"(tb));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = __uint_as_float(r[i]);
+        w[i] = __uint_as_float(q[i]);
+    }
+}
+
 // byte offset of element (row, col) inside a [rows x KDIM] fp32 operand stored as KDIM/32 blocks of
 // [rows x 32] in the canonical K-major SWIZZLE_128B layout
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows)
