@@ -6,9 +6,9 @@
 // k that at least one of its rows uses, the producer warps gather the 128 neighbour rows (zeros
 // where a row has no neighbour) into shared memory in the UMMA canonical K-major SWIZZLE_128B
 // layout, while the offset's weight tile arrives by one bulk async copy (TMA unit, cp.async.bulk)
-// from a pre-swizzled image.  A single elected thread issues tcgen05.mma (kind::tf32, M=128,
-// N=Cout, K=8) into a TMEM accumulator; the epilogue reads it back with tcgen05.ld, applies
-// bias + LeakyReLU and writes the rows.
+// from a pre-swizzled image.  A single elected thread issues tcgen05.mma (kind::tf32, M=128, K=8) into a TMEM
+// accumulator; the drain warps read each offset's partial product back with tcgen05.ld and carry the sum over
+// offsets in FP32 registers; bias + LeakyReLU epilogue.
 //
 // FP32 fidelity (the path's parity bound is 1e-4 relative, which plain TF32 misses): split-TF32.
 // Each operand is split as x ~ hi + lo with hi = RN_tf32(x) and lo = RN_tf32(x - hi) (|lo| <= 2^-12 |x|; rounding
@@ -18,15 +18,44 @@
 // are made while staging (A) / in the weight prep kernel (B), so the tensor core only ever sees
 // operands that are already TF32-exact (no dependence on how the hardware would round).
 //
-// Pipeline (mbarriers): a step stages 32 input channels of one offset; full[2] (producers +
-// bulk-copy bytes -> MMA), empty[2] (tcgen05.commit -> producers), tfull[2] / tempty[2]
-// (double-buffered TMEM accumulator: MMA <-> drain warps).  Two 48 KB stages per CTA, two CTAs per SM
-// (measured faster than four stages with one CTA per SM: 51 vs 58 us on the 19.6k-row 64->64 layer).
-// Small levels are split over gridDim.y CTAs per tile (disjoint offsets) so all 148 SMs have work.
+// Pipeline (mbarriers): a step stages 32 input channels of one offset; full[2] (producer group + bulk-copy bytes
+// -> MMA), empty[2] (tcgen05.commit -> producers), tfull[2] / tempty[2] (double-buffered TMEM accumulator: MMA <->
+// drain warps).  Two 48 KB stages per CTA, two CTAs per SM.  Warp roles (544 threads, 56 registers):
+//   warps 0-3 / 4-7  two producer groups, one per stage, working on alternating steps (a step is a serial chain of
+//                    index lookup, gather, split, store, proxy fence, arrive: two chains in flight per CTA);
+//   warp 8           TMEM owner; one elected lane (elect.sync: operands in uniform registers) issues per K block
+//                    A_hi x [B_hi | B_lo] as ONE MMA of N = 2 Cout and A_lo x B_hi into the first half;
+//   warps 9-16       drain + epilogue, two warps per TMEM lane quarter with half of the columns each.
+// Levels whose tile count does not fill whole rounds of 296 resident CTAs are split over gridDim.y CTAs per tile
+// (disjoint offsets), see tc_split_for.
 #include "tc_common.cuh"
 
 #ifndef TC_DIAG
 #define TC_DIAG 0      // 1..5: timing-only diagnostics (scripts/diag_tc.sh); results are wrong when non-zero
+#endif
+
+#ifdef TC_TRACE          // per-CTA phase time stamps (scripts/tc_trace.py); never defined in the shipped build
+__device__ unsigned long long g_tc_trace[8 * 4096];
+#define TC_STAMP(slot)                                                                          \
+    do {                                                                                        \
+        if (blockIdx.x + gridDim.x * blockIdx.y < 4096) {                                       \
+            unsigned long long t_;                                                              \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+            g_tc_trace[8 * (blockIdx.x + gridDim.x * blockIdx.y) + (slot)] = t_;                \
+        }                                                                                       \
+    } while (0)
+__device__ unsigned long long g_tc_steps[6 * 64];       // CTA 0: per-step stamps of each role
+#define TC_STEP_STAMP(role, st)                                                                 \
+    do {                                                                                        \
+        if (blockIdx.x == 7 && blockIdx.y == 0 && (st) < 64) {                                  \
+            unsigned long long t_;                                                              \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+            g_tc_steps[(role) * 64 + (st)] = t_;                                                \
+        }                                                                                       \
+    } while (0)
+#else
+#define TC_STAMP(slot) do { } while (0)
+#define TC_STEP_STAMP(role, st) do { } while (0)
 #endif
 
 namespace rslo {
@@ -39,6 +68,9 @@ constexpr int TC_ROWS = 128;
 // CTAs per SM within the register file, 8 drain warps that own half of the accumulator columns each.
 constexpr int TC_PRODUCER_WARPS = 8;       // warps 0..7: gather
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
+constexpr int TC_KS = 32;                  // K channels staged per pipeline step (one 128-byte swizzle row)
+constexpr int TC_STAGES = 2;
+constexpr int TC_GROUP_WARPS = TC_PRODUCER_WARPS / TC_STAGES;    // producer warps per stage
 constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;        // warp 8: TMEM owner and MMA issuer
 constexpr int TC_DRAIN_WARPS = 8;          // warps 9..16: drain + epilogue (two per TMEM lane quarter)
 constexpr int TC_DRAINERS = TC_DRAIN_WARPS * 32;
@@ -70,9 +102,6 @@ __global__ void k_tc_prep(const float* __restrict__ W, int K, int Cin, int Cout,
     *(float*)(base + off) = hi;
     *(float*)(base + (size_t)ntile * 128 + off) = lo;
 }
-
-constexpr int TC_KS = 32;                  // K channels staged per pipeline step (one 128-byte swizzle row)
-constexpr int TC_STAGES = 2;
 
 template <int KDIM, int NDIM>
 struct TcSmem {
@@ -119,12 +148,13 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     const int wtile = blockIdx.x * gridDim.z + ntile;          // work tile id (rows x channel slice)
     bimg += (size_t)ntile * K * NSUB * (2 * S::B_BYTES / 4);
     if (row0 >= n) return;                    // uniform per CTA (all splits of the tile agree)
+    if (tid == 0) TC_STAMP(0);
     // two accumulator buffers of 2 * NDIM columns each: [A_hi B_hi + A_lo B_hi | A_hi B_lo] (64, 128 or 256 columns)
     constexpr int TCOLS = 4 * NDIM;
 
     if (tid == 0) {
         for (int i = 0; i < TC_STAGES; ++i) {
-            mbar_init(full_bar + i, TC_PRODUCERS);
+            mbar_init(full_bar + i, TC_GROUP_WARPS * 32);
             mbar_init(empty_bar + i, 1);
         }
         mbar_init(tfull_bar + 0, 1);
@@ -173,6 +203,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
             s_klist[j] = __ffs(m) - 1;
             m &= m - 1;
         }
+        TC_STAMP(1);
     }
     __syncthreads();
 
@@ -180,21 +211,26 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
         // ================= producers: gather neighbour rows, split to TF32 hi/lo, swizzled store =================
         constexpr int CHUNKS = TC_KS / 4;                // 16-byte chunks per staged row segment (128 B)
         constexpr int ROWS_PER_LD = 32 / CHUNKS;         // 4 rows per warp-wide load
-        constexpr int ROWS_PER_WARP = TC_ROWS / TC_PRODUCER_WARPS;       // 16
-        constexpr int NLD = ROWS_PER_WARP / ROWS_PER_LD; // 4 loads per thread per step, all in flight together
+        // One producer group per pipeline stage; the groups work on alternating steps.  A step is a serial chain per
+        // warp (index lookup -> gather -> split -> store -> proxy fence -> arrive: ~1.1 us measured with every warp on
+        // every step, profiles/r02_tc_kernel_diagnostics.md), so two independent chains in flight are worth more than
+        // twice the threads on one.
+        constexpr int ROWS_PER_WARP = TC_ROWS / TC_GROUP_WARPS;          // 32
+        constexpr int NLD = ROWS_PER_WARP / ROWS_PER_LD; // 8 loads per thread per step, all in flight together
+        const int grp = warp / TC_GROUP_WARPS, gw = warp % TC_GROUP_WARPS;
         const int sub = lane / CHUNKS, c = lane % CHUNKS;
         const uint32_t smem_base = smem_u32(smem);
         // per-thread swizzled store offsets of its NLD row segments (same for every step)
         uint32_t soff[NLD];
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) soff[j] = sw128_offset(warp * ROWS_PER_WARP + j * ROWS_PER_LD + sub, c * 4, TC_ROWS);
+        for (int j = 0; j < NLD; ++j) soff[j] = sw128_offset(gw * ROWS_PER_WARP + j * ROWS_PER_LD + sub, c * 4, TC_ROWS);
         int nsteps = __popc(mask) * NSUB;
 
         // gather of step st: NLD independent 16-byte loads (zeros for rows without this neighbour)
         auto gather = [&](int k, int h, float4(&v)[NLD]) {
 #pragma unroll
             for (int j = 0; j < NLD; ++j) {
-                const int r = warp * ROWS_PER_WARP + j * ROWS_PER_LD + sub;
+                const int r = gw * ROWS_PER_WARP + j * ROWS_PER_LD + sub;
                 const int src = s_nbr[r * K + k];
                 v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #if TC_DIAG != 3
@@ -203,15 +239,17 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
 #endif
             }
         };
-        // split to TF32 {hi, lo} and store into stage s in the UMMA layout; then publish the stage
-        auto publish = [&](int st, int k, int h, const float4(&v)[NLD]) {
+        // split to TF32 {hi, lo} and store into stage s in the UMMA layout
+        auto stage_store = [&](int st, int k, int h, const float4(&v)[NLD]) {
             const int s = st % TC_STAGES;
+            if (gw == 0 && lane == 0) TC_STEP_STAMP(0, st);       // about to wait for the stage
             mbar_wait(empty_bar + s, ((st / TC_STAGES) & 1) ^ 1);
+            if (gw == 0 && lane == 0) TC_STEP_STAMP(1, st);       // stage free
             const uint32_t stage = smem_base + s * S::STAGE_BYTES;
 #if TC_DIAG == 1
-            if (warp == 0 && st < TC_STAGES && elect_one()) {
+            if (gw == 0 && st < TC_STAGES && elect_one()) {
 #else
-            if (warp == 0 && elect_one()) {      // one lane, uniform operands for the bulk copy
+            if (gw == 0 && elect_one()) {        // one lane, uniform operands for the bulk copy
 #endif
                 mbar_expect_tx(full_bar + s, 2 * S::B_BYTES);
                 bulk_copy_g2s(smem + s * S::STAGE_BYTES + 2 * S::A_BYTES,
@@ -228,20 +266,30 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 sts128(stage + soff[j], hh);
                 sts128(stage + S::A_BYTES + soff[j], ll);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-            mbar_arrive(full_bar + s);
         };
-        // software pipeline: the loads of step st+1 are in flight while step st is split and stored
-        // (two rotating register buffers; measured: the producers, not the MMAs, pace this kernel)
+        // make the stores visible to the tensor core's (async-proxy) reads and hand the stage over
+        auto publish = [&](int st) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(full_bar + st % TC_STAGES);
+            if (gw == 0 && lane == 0) TC_STEP_STAMP(2, st);       // published
+        };
+        // this group's steps: grp, grp + TC_STAGES, ... (always stage `grp`); the loads of its next step are issued
+        // right after the hand-over and are in flight while the other group stores and publishes (issuing them before
+        // the proxy fence measured 2-5 % slower)
         auto kof = [&](int st) { return s_klist[st / NSUB]; };
-        float4 va[NLD], vb[NLD];
-        if (nsteps > 0) gather(kof(0), 0, va);
-        for (int st = 0; st < nsteps; st += 2) {
-            if (st + 1 < nsteps) gather(kof(st + 1), (st + 1) % NSUB, vb);
-            publish(st, kof(st), st % NSUB, va);
-            if (st + 1 >= nsteps) break;
-            if (st + 2 < nsteps) gather(kof(st + 2), (st + 2) % NSUB, va);
-            publish(st + 1, kof(st + 1), (st + 1) % NSUB, vb);
+        float4 va[NLD];
+        int st = grp;
+        if (st < nsteps) gather(kof(st), st % NSUB, va);
+        for (; st < nsteps; st += TC_STAGES) {
+            stage_store(st, kof(st), st % NSUB, va);
+            publish(st);
+            if (st + TC_STAGES < nsteps) gather(kof(st + TC_STAGES), (st + TC_STAGES) % NSUB, va);
+        }
+        if (tid == 0) {
+            TC_STAMP(2);
+#ifdef TC_TRACE
+            g_tc_trace[8 * (blockIdx.x + gridDim.x * blockIdx.y) + 6] = nsteps;
+#endif
         }
     } else if (warp == TC_MMA_WARP) {
         // ================= MMA issuer (one elected lane) =================
@@ -264,6 +312,7 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                 for (int h = 0; h < NSUB; ++h) {
                     const int st = it * NSUB + h, s = st % TC_STAGES;
                     mbar_wait(full_bar + s, (st / TC_STAGES) & 1);    // operands staged
+                    TC_STEP_STAMP(3, st);                             // MMA warp saw the stage
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
                     const uint32_t a_lo = a_hi + S::A_BYTES;
@@ -279,9 +328,11 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
                         umma_tf32(d, umma_desc_k_sw128(a_lo + kk * 32), umma_desc_k_sw128(b_hi + kk * 32), idesc, 1u);
 #endif
                     umma_commit(empty_bar + s);        // stage reusable once these MMAs retire
+                    TC_STEP_STAMP(4, st);                             // MMAs issued
                 }
                 umma_commit(tfull_bar + buf);          // this offset's partial product is complete
             }
+            TC_STAMP(3);
         }
         __syncwarp();
     } else {
@@ -314,7 +365,9 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
 #endif
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty_bar + buf);
+            if (warp == TC_MMA_WARP + 1 && lane == 0) TC_STEP_STAMP(5, it);   // offset drained
         }
+        if (warp == TC_MMA_WARP + 1 && lane == 0) TC_STAMP(4);
         bool finish = true;
         if (split > 1) {
             float4* mine = reinterpret_cast<float4*>(scratch + ((size_t)(wtile * split + sidx) * TC_ROWS + r) * NDIM + half * HC);
@@ -361,13 +414,16 @@ k_spconv_tc(const float* __restrict__ in, const int* __restrict__ nbr, int n_cap
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) TC_STAMP(5);
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
     }
 }
 
 // Offsets of a tile are split over `split` CTAs when the level is too small to fill the GPU (two CTAs
-// are resident per SM): the largest split in 1..4 that keeps the whole grid in one wave.
+// are resident per SM): the largest split in 1..4 that keeps the whole grid in one round of 296 CTAs.  (A cost model
+// that also splits levels of slightly more than 296 tiles into three rounds of half tiles was tried and measured
+// slower, 107 vs 97 us at 318 tiles: the few CTAs of a last partial round run alone on their SMs and finish early.)
 static inline int tc_split_for(int n_cap, int ntiles)
 {
     const int tiles = cdiv(n_cap, TC_ROWS) * ntiles;
@@ -418,6 +474,17 @@ static inline bool tc_kdim_ok(int kdim)
 }  // namespace rslo
 
 using namespace rslo;
+
+#ifdef TC_TRACE
+extern "C" int rslo_debug_tc_trace(unsigned long long* host, int n_words)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(unsigned long long) * n_words);
+}
+extern "C" int rslo_debug_tc_steps(unsigned long long* host)
+{
+    return (int)cudaMemcpyFromSymbol(host, g_tc_steps, sizeof(unsigned long long) * 6 * 64);
+}
+#endif
 
 extern "C" int rslo_spconv_tc_supported(int Cin, int Cout, int K)
 {
