@@ -37,6 +37,31 @@ namespace {
 using namespace tc;
 
 constexpr int CV_ROWS = 128;
+#ifdef TC_TRACE          // per-CTA / per-stage time stamps (scripts/cv_trace.py); never defined in the shipped build
+__device__ unsigned long long g_cv_trace[8 * 2048];
+__device__ unsigned long long g_cv_steps[6 * 64];
+#define CV_STAMP(slot)                                                                                       \
+    do {                                                                                                     \
+        const int cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                      \
+        if (cta_ < 2048) {                                                                                   \
+            unsigned long long t_;                                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+            g_cv_trace[8 * cta_ + (slot)] = t_;                                                              \
+        }                                                                                                    \
+    } while (0)
+#define CV_STEP_STAMP(role, st)                                                                              \
+    do {                                                                                                     \
+        if (blockIdx.x == 5 && blockIdx.y == 0 && blockIdx.z == 0 && (st) < 64) {                            \
+            unsigned long long t_;                                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+            g_cv_steps[(role) * 64 + (st)] = t_;                                                             \
+        }                                                                                                    \
+    } while (0)
+#else
+#define CV_STAMP(slot) do { } while (0)
+#define CV_STEP_STAMP(role, st) do { } while (0)
+#endif
+
 constexpr int CV_THREADS = 192;
 constexpr int CV_KS = 32;                       // channels per stage (one 128-byte swizzle row)
 constexpr int CV_A_BYTES = CV_ROWS * CV_KS * 4;  // one plane of the pixel tile: 16 KB
@@ -108,6 +133,12 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int nsteps = HALO ? (3 * P.kchunks - sidx + split - 1) / split : ntaps_mine * P.kchunks;
     const int group = HALO ? 1 : P.group;
     const int ngroups = (nsteps + group - 1) / group;
+    if (tid == 0) {
+        CV_STAMP(0);
+#ifdef TC_TRACE
+        g_cv_trace[8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + 6] = nsteps;
+#endif
+    }
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -133,6 +164,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
+    if (tid == 0) CV_STAMP(1);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -144,6 +176,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const int item = sidx + st * split, dwi = item % 3, kc = item / 3;
                     const int s = st % STAGES;
                     mbar_wait(empty_bar + s, ((st / STAGES) & 1) ^ 1);
+                    CV_STEP_STAMP(0, st);                          // stage free
                     const uint32_t a = base + s * S::STAGE_BYTES;
                     tma::mbar_arrive_expect_tx(full_bar + s, S::STAGE_BYTES);
                     tma::load_5d(a, &tmA, kc * CV_KS, w0 + dwi - 1, 0, h0 - 1, b, full_bar + s);
@@ -181,7 +214,9 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int st = 0; st < nsteps; ++st) {
                     const int buf = st & 1, s = st % STAGES;
                     mbar_wait(tempty_bar + buf, ((st >> 1) & 1) ^ 1);
+                    CV_STEP_STAMP(1, st);                          // accumulator buffer free
                     mbar_wait(full_bar + s, (st / STAGES) & 1);
+                    CV_STEP_STAMP(2, st);                          // operands landed
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d = tmem_base + buf * NT;
                     const uint32_t sb = smem_u32(smem) + s * S::STAGE_BYTES;
@@ -203,6 +238,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                     umma_commit(empty_bar + s);
                     umma_commit(tfull_bar + buf);
+                    CV_STEP_STAMP(3, st);                          // MMAs issued
                 }
             }
             for (int st = 0; st < (HALO ? 0 : nsteps); ++st) {
@@ -245,6 +281,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int g = 0; g < ngroups; ++g) {
             const int buf = g & 1;
             mbar_wait(tfull_bar + buf, (g >> 1) & 1);
+            if (warp == 2 && lane == 0) CV_STEP_STAMP(4, g);       // MMAs of the stage retired
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NT;
 #pragma unroll
@@ -256,7 +293,9 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty_bar + buf);
+            if (warp == 2 && lane == 0) CV_STEP_STAMP(5, g);       // drained
         }
+        if (warp == 2 && lane == 0) CV_STAMP(4);
         bool finish = true;
         if (split > 1) {
             const int wtile = blockIdx.x * gridDim.z + blockIdx.z;
@@ -335,6 +374,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) CV_STAMP(5);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S::TCOLS) : "memory");
     }
@@ -877,6 +917,20 @@ __global__ void k_wgrad_finish(const float* __restrict__ dW, int Cout, int CoutP
 }  // namespace rslo
 
 using namespace rslo;
+
+#ifdef TC_TRACE
+extern "C" int rslo_debug_cv_trace(unsigned long long* ctas, unsigned long long* steps)
+{
+    cudaMemcpyFromSymbol(ctas, g_cv_trace, sizeof(g_cv_trace));
+    return (int)cudaMemcpyFromSymbol(steps, g_cv_steps, sizeof(g_cv_steps));
+}
+extern "C" int rslo_debug_cv_clear()
+{
+    static unsigned long long z[8 * 2048];
+    cudaMemcpyToSymbol(g_cv_trace, z, sizeof(g_cv_trace));
+    return (int)cudaMemcpyToSymbol(g_cv_steps, z, sizeof(g_cv_steps));
+}
+#endif
 
 extern "C" int rslo_conv2d_tc_supported(int Cin, int Cout, int ksize, int stride)
 {
