@@ -34,6 +34,34 @@ extern unsigned long long g_launch_count;
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The head runs ~880 kernels of 3-40 us per step from two CUDA graphs; the ~2 us between dependent kernel nodes is a
+// visible share of it.  Kernels launched through launch_pdl() may be made resident while their predecessor in the
+// stream is still running: every such kernel calls pdl_launch_dependents() at its top (the NEXT kernel may start to
+// launch once all CTAs of this one have started) and pdl_wait() before its first access to global memory (blocks until
+// the PREVIOUS grid has completed and its writes are visible).  Both are no-ops in a kernel launched the ordinary way.
+// RSLO_PDL=0 in the environment turns the launch attribute off.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Bump allocator over a caller-provided workspace (256 B aligned slices).
 struct Workspace {
     char* base;

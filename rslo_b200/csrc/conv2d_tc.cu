@@ -108,6 +108,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ ConvParams P, const float* __restrict__ bias, float* __restrict__ out,
             float* __restrict__ scratch, int* __restrict__ tile_counter, double* __restrict__ stats)
 {
+    pdl_launch_dependents();
     using S = CvCfg<NT, HALO>;
     constexpr int STAGES = S::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -164,6 +165,7 @@ k_conv2d_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
+    pdl_wait();          // barriers, TMEM and descriptors are set up; global memory is touched from here on
     if (tid == 0) CV_STAMP(1);
 
     if (warp == 0) {
@@ -426,7 +428,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmW, const Con
         configured = true;
     }
     RSLO_COUNT();
-    k_conv2d_tc<NT, HALO><<<dim3(tiles, split, ntiles), CV_THREADS, S::TOTAL, st>>>(tmA, tmW, P, bias, out, scratch, counter,
+    launch_pdl(k_conv2d_tc<NT, HALO>, dim3(tiles, split, ntiles), CV_THREADS, S::TOTAL, st, tmA, tmW, P, bias, out, scratch, counter,
                                                                                  stats);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc");
     return 0;
@@ -655,6 +657,8 @@ static int forward_taps(int ks, int s, int C, ConvTap* taps)
 // ---- elementwise helpers ---------------------------------------------------------------------------
 __global__ void k_split_planes(const float4* __restrict__ x, size_t n4, float4* __restrict__ hi, float4* __restrict__ lo)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = __ldg(x + i);
         const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
@@ -669,6 +673,8 @@ __global__ void k_split_planes(const float4* __restrict__ x, size_t n4, float4* 
 __global__ void k_conv2d_wprep(const float* __restrict__ w, int Cout, int CoutP, int Cin, int taps, int mode,
                                float* __restrict__ img)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int total = taps * CoutP * Cin;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -731,6 +737,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 k_conv2d_wgrad_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                   const __grid_constant__ WgradParams P, float* __restrict__ dW)
 {
+    pdl_launch_dependents();
     using S = WgCfg<NT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -778,6 +785,7 @@ k_conv2d_wgrad_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
+    pdl_wait();          // barriers, TMEM and descriptors are set up; global memory is touched from here on
     const int per_img = P.tiles_h * P.tiles_w;
 
     if (warp == 0) {
@@ -896,7 +904,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, const Wg
         configured = true;
     }
     RSLO_COUNT();
-    k_conv2d_wgrad_tc<NT><<<grid, WG_THREADS, S::TOTAL, st>>>(tmX, tmG, P, dW);
+    launch_pdl(k_conv2d_wgrad_tc<NT>, grid, WG_THREADS, S::TOTAL, st, tmX, tmG, P, dW);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc_backward_weight");
     return 0;
 }
@@ -905,6 +913,8 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, const Wg
 __global__ void k_wgrad_finish(const float* __restrict__ dW, int Cout, int CoutP, int Cin, int taps, int accumulate,
                                float* __restrict__ gw)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int total = taps * Cout * Cin;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;         // OIHW index (real output channels only)
     if (i >= total) return;
@@ -948,7 +958,7 @@ extern "C" int rslo_conv2d_split(const float* x, size_t n, float* split_pair, rs
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     RSLO_COUNT();
-    k_split_planes<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, n4, (float4*)split_pair, (float4*)(split_pair + n));
+    launch_pdl(k_split_planes, blocks, 256, 0, (cudaStream_t)stream, (const float4*)x, n4, (float4*)split_pair, (float4*)(split_pair + n));
     RSLO_CHECK_LAUNCH("rslo_conv2d_split");
     return 0;
 }
@@ -959,7 +969,7 @@ extern "C" int rslo_conv2d_tc_prepare(const float* weight_oihw, int Cout, int Co
     if (Cout_padded < Cout) Cout_padded = Cout;
     const int total = ksize * ksize * Cout_padded * Cin;
     RSLO_COUNT();
-    k_conv2d_wprep<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(weight_oihw, Cout, Cout_padded, Cin, ksize * ksize,
+    launch_pdl(k_conv2d_wprep, cdiv(total, 256), 256, 0, (cudaStream_t)stream, weight_oihw, Cout, Cout_padded, Cin, ksize * ksize,
                                                                       mode, image);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc_prepare");
     return 0;
@@ -1095,7 +1105,7 @@ extern "C" int rslo_conv2d_tc_backward_weight(const float* x_split, const float*
     if (Cout_real <= 0 || Cout_real > Cout) Cout_real = Cout;
     const int total = P.ntaps * Cin * Cout_real;
     RSLO_COUNT();
-    k_wgrad_finish<<<cdiv(total, 256), 256, 0, st>>>(scratch, Cout_real, Cout, Cin, P.ntaps, accumulate, grad_weight_oihw);
+    launch_pdl(k_wgrad_finish, cdiv(total, 256), 256, 0, st, scratch, Cout_real, Cout, Cin, P.ntaps, accumulate, grad_weight_oihw);
     RSLO_CHECK_LAUNCH("rslo_conv2d_tc_backward_weight(finish)");
     return 0;
 }

@@ -35,6 +35,8 @@ __device__ __forceinline__ void split4(const float4& v, float4& h, float4& l)
 __global__ void k_head_pack(const float* __restrict__ x1, const float* __restrict__ x2, int C, int HW, float* __restrict__ hi,
                             float* __restrict__ lo, float* __restrict__ mask)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     __shared__ float psum[8][32];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -76,6 +78,8 @@ __global__ void k_head_pack(const float* __restrict__ x1, const float* __restric
 // NHWC gradient [B][HW][2C] -> NCHW gradients of the two frames.  grid (ceil(HW/32), 2C/32, B), block (32, 8)
 __global__ void k_head_unpack(const float* __restrict__ dx, int C, int HW, float* __restrict__ g1, float* __restrict__ g2)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int p0 = blockIdx.x * 32, ct = blockIdx.y, b = blockIdx.z;
@@ -102,6 +106,8 @@ k_bn_act_fwd(const float* __restrict__ y, int HW, int C, int ipg, int G, int chu
              const float* __restrict__ residual, int relu, float* __restrict__ z, float* __restrict__ zhi,
              float* __restrict__ zlo, float* __restrict__ mean_rstd)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     float* s_mean = sm;
     float* s_rs = sm + C;
@@ -192,6 +198,8 @@ __global__ void __launch_bounds__(HE_THREADS)
 k_bn_bwd_reduce(const float* __restrict__ dz, const float* __restrict__ z, const float* __restrict__ y, int HW, int C, int ipg,
                 int chunk, const float* __restrict__ mean_rstd, int relu, double* __restrict__ sums)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float4 red[2][HE_THREADS];
     const int b = blockIdx.y, g = b / ipg;
     const int c4n = C >> 2;
@@ -243,6 +251,8 @@ k_bn_bwd_apply(const float* __restrict__ dz, const float* __restrict__ z, const 
                float* __restrict__ dres, int dres_add, float* __restrict__ dgamma, float* __restrict__ dbeta,
                float* __restrict__ dbias)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     float* s_mean = sm;
     float* s_rstd = sm + C;
@@ -324,6 +334,8 @@ k_bn_bwd_apply(const float* __restrict__ dz, const float* __restrict__ z, const 
 __global__ void k_upcat_split(const float4* __restrict__ z, int B, int H, int W, int c4n, int u, int ld4, int choff4,
                               float4* __restrict__ hi, float4* __restrict__ lo)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)B * H * W * c4n;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % c4n);
@@ -345,6 +357,8 @@ __global__ void k_upcat_split(const float4* __restrict__ z, int B, int H, int W,
 __global__ void k_upcat_bwd(const float4* __restrict__ dcat, int B, int H, int W, int c4n, int u, int ld4, int choff4,
                             float4* __restrict__ dz, int add)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)B * H * W * c4n;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % c4n);
@@ -370,6 +384,8 @@ __global__ void k_upcat_bwd(const float4* __restrict__ dcat, int B, int H, int W
 // bias gradient of a narrow output convolution: out[c] += sum_rows g[row][c], c < C <= 32 (out pre-zeroed)
 __global__ void k_bias_grad(const float* __restrict__ g, int N, int ld, int C, float* __restrict__ out)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[8][32];
     const int c = threadIdx.x & 31, l = threadIdx.x >> 5;
     float s = 0.f;
@@ -390,6 +406,8 @@ __global__ void k_bias_grad(const float* __restrict__ g, int N, int ld, int C, f
 // grid (blocks, n_layers)
 __global__ void k_multi_prepare(const rslo_conv_prep_t* __restrict__ tab)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const rslo_conv_prep_t e = tab[blockIdx.y];
     const int total = e.taps * e.CoutP * e.Cin;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -416,6 +434,8 @@ __global__ void k_multi_prepare(const rslo_conv_prep_t* __restrict__ tab)
 // dW [taps][Cin][CoutP] -> OIHW gradient [Cout][Cin][taps].  grid (blocks, n_layers)
 __global__ void k_multi_wgrad_finish(const rslo_wgrad_finish_t* __restrict__ tab)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const rslo_wgrad_finish_t e = tab[blockIdx.y];
     const int total = e.taps * e.Cout * e.Cin;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -455,7 +475,7 @@ extern "C" int rslo_head_pack_input(const float* x1, const float* x2, int B, int
     if (C % 32 != 0) return bad("rslo_head_pack_input: C must be a multiple of 32");
     const size_t plane = (size_t)B * HW * 2 * C;
     RSLO_COUNT();
-    k_head_pack<<<dim3(cdiv(HW, 32), B), dim3(32, 8), 0, (cudaStream_t)stream>>>(x1, x2, C, HW, split_pair, split_pair + plane, mask);
+    launch_pdl(k_head_pack, dim3(cdiv(HW, 32), B), dim3(32, 8), 0, (cudaStream_t)stream, x1, x2, C, HW, split_pair, split_pair + plane, mask);
     RSLO_CHECK_LAUNCH("rslo_head_pack_input");
     return 0;
 }
@@ -464,7 +484,7 @@ extern "C" int rslo_head_unpack_grad(const float* dx, int B, int C, int HW, floa
 {
     if (C % 32 != 0) return bad("rslo_head_unpack_grad: C must be a multiple of 32");
     RSLO_COUNT();
-    k_head_unpack<<<dim3(cdiv(HW, 32), 2 * C / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(dx, C, HW, g1, g2);
+    launch_pdl(k_head_unpack, dim3(cdiv(HW, 32), 2 * C / 32, B), dim3(32, 8), 0, (cudaStream_t)stream, dx, C, HW, g1, g2);
     RSLO_CHECK_LAUNCH("rslo_head_unpack_grad");
     return 0;
 }
@@ -480,7 +500,7 @@ extern "C" int rslo_bn_act_forward(const float* y, int B, int HW, int C, int img
     const int chunk = pick_chunk(HW, C / 4, B);
     const size_t plane = (size_t)B * HW * C;
     RSLO_COUNT();
-    k_bn_act_fwd<<<dim3(cdiv(HW, chunk), B), HE_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
+    launch_pdl(k_bn_act_fwd, dim3(cdiv(HW, chunk), B), HE_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream, 
         y, HW, C, imgs_per_group, B / imgs_per_group, chunk, stats, gamma, beta, running_mean, running_var, num_batches_tracked,
         eps, momentum, update_repeat, residual, relu, z, z_split, z_split ? z_split + plane : nullptr, mean_rstd);
     RSLO_CHECK_LAUNCH("rslo_bn_act_forward");
@@ -499,10 +519,10 @@ extern "C" int rslo_bn_act_backward(const float* dz, const float* z, const float
     const int chunk = pick_chunk(HW, c4n, B);
     const size_t plane = (size_t)B * HW * C;
     RSLO_COUNT();
-    k_bn_bwd_reduce<<<dim3(cdiv(HW, chunk), B), HE_THREADS, 0, st>>>(dz, z, y, HW, C, imgs_per_group, chunk, mean_rstd, relu, sums);
+    launch_pdl(k_bn_bwd_reduce, dim3(cdiv(HW, chunk), B), HE_THREADS, 0, st, dz, z, y, HW, C, imgs_per_group, chunk, mean_rstd, relu, sums);
     RSLO_CHECK_LAUNCH("rslo_bn_act_backward(reduce)");
     RSLO_COUNT();
-    k_bn_bwd_apply<<<dim3(cdiv(HW, chunk), B), HE_THREADS, 5 * C * sizeof(float), st>>>(
+    launch_pdl(k_bn_bwd_apply, dim3(cdiv(HW, chunk), B), HE_THREADS, 5 * C * sizeof(float), st, 
         dz, z, y, HW, C, imgs_per_group, B / imgs_per_group, chunk, mean_rstd, gamma, sums, relu, batch_stats, g_split,
         g_split + plane, dres, dres_accumulate, dgamma, dbeta, dbias);
     RSLO_CHECK_LAUNCH("rslo_bn_act_backward(apply)");
@@ -518,7 +538,7 @@ extern "C" int rslo_upcat_split(const float* z, int B, int H, int W, int C, int 
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     RSLO_COUNT();
-    k_upcat_split<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)z, B, H, W, C / 4, up, ld / 4, choff / 4,
+    launch_pdl(k_upcat_split, blocks, 256, 0, (cudaStream_t)stream, (const float4*)z, B, H, W, C / 4, up, ld / 4, choff / 4,
                                                            (float4*)dst_split, (float4*)(dst_split + plane));
     RSLO_CHECK_LAUNCH("rslo_upcat_split");
     return 0;
@@ -532,7 +552,7 @@ extern "C" int rslo_upcat_backward(const float* dcat, int B, int H, int W, int C
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     RSLO_COUNT();
-    k_upcat_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)dcat, B, H, W, C / 4, up, ld / 4, choff / 4, (float4*)dz,
+    launch_pdl(k_upcat_bwd, blocks, 256, 0, (cudaStream_t)stream, (const float4*)dcat, B, H, W, C / 4, up, ld / 4, choff / 4, (float4*)dz,
                                                          accumulate);
     RSLO_CHECK_LAUNCH("rslo_upcat_backward");
     return 0;
@@ -545,7 +565,7 @@ extern "C" int rslo_bias_grad(const float* g, int N, int ld, int C, float* out, 
     if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
     RSLO_COUNT();
-    k_bias_grad<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, N, ld, C, out);
+    launch_pdl(k_bias_grad, blocks, 256, 0, (cudaStream_t)stream, g, N, ld, C, out);
     RSLO_CHECK_LAUNCH("rslo_bias_grad");
     return 0;
 }
@@ -554,7 +574,7 @@ extern "C" int rslo_conv2d_multi_prepare(const rslo_conv_prep_t* table_dev, int 
 {
     if (n <= 0) return 0;
     RSLO_COUNT();
-    k_multi_prepare<<<dim3(24, n), 256, 0, (cudaStream_t)stream>>>(table_dev);
+    launch_pdl(k_multi_prepare, dim3(24, n), 256, 0, (cudaStream_t)stream, table_dev);
     RSLO_CHECK_LAUNCH("rslo_conv2d_multi_prepare");
     return 0;
 }
@@ -563,7 +583,7 @@ extern "C" int rslo_conv2d_multi_wgrad_finish(const rslo_wgrad_finish_t* table_d
 {
     if (n <= 0) return 0;
     RSLO_COUNT();
-    k_multi_wgrad_finish<<<dim3(24, n), 256, 0, (cudaStream_t)stream>>>(table_dev);
+    launch_pdl(k_multi_wgrad_finish, dim3(24, n), 256, 0, (cudaStream_t)stream, table_dev);
     RSLO_CHECK_LAUNCH("rslo_conv2d_multi_wgrad_finish");
     return 0;
 }

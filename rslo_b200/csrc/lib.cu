@@ -1,4 +1,5 @@
 // Library-level entry points: ABI version and last-error text.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -9,6 +10,14 @@ unsigned long long g_launch_count = 0;
 void set_last_error(const char* what, cudaError_t e)
 {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+}
+bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("RSLO_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 }  // namespace rslo
 
