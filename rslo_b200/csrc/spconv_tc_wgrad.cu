@@ -24,6 +24,7 @@ using namespace tc;
 constexpr int WG_STEP = 64;                // rows per pipeline step (8 MMAs of K = 8 per split term)
 constexpr int WG_PRODUCER_WARPS = 8;
 constexpr int WG_PRODUCERS = WG_PRODUCER_WARPS * 32;
+constexpr int WG_GROUP = WG_PRODUCERS / 2;          // two producer groups, one per A stage, on alternating items
 constexpr int WG_THREADS = (WG_PRODUCER_WARPS + 1 + 4) * 32;   // + MMA warp + 4 drain warps
 constexpr int WG_ASTAGES = 2;
 constexpr int WG_GSTAGES = 2;
@@ -98,9 +99,9 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(a_full + i, WG_PRODUCERS);
+            mbar_init(a_full + i, WG_GROUP);
             mbar_init(a_empty + i, 1);
-            mbar_init(g_full + i, WG_PRODUCERS);
+            mbar_init(g_full + i, WG_GROUP);
             mbar_init(g_empty + i, 1);
         }
         mbar_init(acc_bar, 1);
@@ -118,17 +119,23 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
 
     if (warp < WG_PRODUCER_WARPS) {
         // ================= producers =================
+        // Two groups of 4 warps, one per A stage, work on alternating (step, group) items: an item is a serial chain
+        // (neighbour index -> gathered row -> stage wait -> split -> store -> proxy fence -> arrive), so two chains in
+        // flight keep the tensor pipe fed (same finding as in spconv_tc.cu).  The group that owns the first item of a
+        // step also stages the step's gradient tile.
         const uint32_t sA_u = smem_u32(sA), sG_u = smem_u32(sG);
-        int item = 0;                                                // (step, group) counter for the A ring
-        for (int st = 0; st < nsteps; ++st) {
+        const int grp = warp / (WG_PRODUCER_WARPS / 2), gt = tid - grp * WG_GROUP;
+        const int nitems = nsteps * ng;
+        for (int item = grp; item < nitems; item += 2) {
+            const int st = item / ng, gi = item - st * ng;
             const int r0 = row_begin + st * WG_STEP;
-            // gradient tile of this step: 64 rows x Cout, once per step
-            {
+            if (gi == 0) {
+                // gradient tile of this step: 64 rows x Cout, once per step
                 const int gs = st & 1;
                 mbar_wait(g_empty + gs, ((st >> 1) & 1) ^ 1);
                 const uint32_t base = sG_u + gs * 2 * C::G_BYTES;
                 constexpr int CH = COUT / 4;                         // 16-byte chunks per row
-                for (int i = tid; i < WG_STEP * CH; i += WG_PRODUCERS) {
+                for (int i = gt; i < WG_STEP * CH; i += WG_GROUP) {
                     const int r = i / CH, c = i % CH;
                     const int o = r0 + r;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -142,16 +149,16 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(g_full + gs);
             }
-            for (int gi = 0; gi < ng; ++gi, ++item) {
-                const int as = item & 1;
+            {
+                const int as = item & 1;                             // == grp
                 const int kbase = (g0 + gi) * C::MEMB;
                 // gather first (loads in flight), then wait for the stage
                 constexpr int CH = 128 / 4;                          // 32 chunks per stacked row
-                constexpr int PER = WG_STEP * CH / WG_PRODUCERS;     // 8 chunks per thread
+                constexpr int PER = WG_STEP * CH / WG_GROUP;         // 16 chunks per thread
                 float4 v[PER];
 #pragma unroll
                 for (int j = 0; j < PER; ++j) {
-                    const int i = tid + j * WG_PRODUCERS;
+                    const int i = gt + j * WG_GROUP;
                     const int r = i / CH, c = i % CH;
                     const int memb = (c * 4) / CIN, cc = (c * 4) % CIN;
                     const int k = kbase + memb;
@@ -165,7 +172,7 @@ k_spconv_tc_wgrad(const float* __restrict__ in, const float* __restrict__ g, con
                 const uint32_t base = sA_u + as * 2 * C::A_BYTES;
 #pragma unroll
                 for (int j = 0; j < PER; ++j) {
-                    const int i = tid + j * WG_PRODUCERS;
+                    const int i = gt + j * WG_GROUP;
                     const int r = i / CH, c = i % CH;
                     const float4 hh = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
                     const float4 ll = make_float4(tf32_rn(v[j].x - hh.x), tf32_rn(v[j].y - hh.y), tf32_rn(v[j].z - hh.z), tf32_rn(v[j].w - hh.w));

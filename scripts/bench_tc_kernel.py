@@ -26,3 +26,12 @@ for key, cin, cout in (("subm2", 64, 64), ("subm1", 32, 32), ("subm3", 64, 64)):
     ev[1].record(); torch.cuda.synchronize()
     R = int((e.nbr[:e.n_out] >= 0).sum())
     print(f"DIAG={os.environ.get('TC_DIAG','0')} {key} rows={e.n_out} R={R} {cin}->{cout}: {ev[0].elapsed_time(ev[1]) / 50 * 1e3:.1f} us")
+    g = torch.randn(e.n_out, cout, device="cuda")
+    for _ in range(3):
+        K.spconv_tc_backward_weight(feat, g, e.nbr, e.n_out, (27, cin, cout))
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(50):
+        K.spconv_tc_backward_weight(feat, g, e.nbr, e.n_out, (27, cin, cout))
+    ev[1].record(); torch.cuda.synchronize()
+    print(f"   wgrad {key} {cin}->{cout}: {ev[0].elapsed_time(ev[1]) / 50 * 1e3:.1f} us")
