@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--cpu-budget-s", type=float, default=420.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     return ap.parse_args()
 
 
