@@ -32,6 +32,11 @@ int rslo_abi_version(void);
 const char* rslo_last_error(void);
 /* Kernels launched by this library in the calling process so far (measurement aid). */
 unsigned long long rslo_kernel_launch_count(void);
+/* The caller is about to capture (on != 0) / has finished capturing (0) the head's launches into a CUDA graph: while
+ * set, the head's kernels are launched with the programmatic-dependent-launch attribute (each of them waits for its
+ * predecessor with griddepcontrol.wait before touching global memory), which removes the launch latency between the
+ * ~880 kernel nodes of the two graphs.  Off by default: on an eager path the attribute costs host time per launch. */
+void rslo_set_graph_capture_hint(int on);
 
 /* ---- a10: exact nearest neighbour ---------------------------------------------------------------
  * Replaces cd.forward_cuda_one_direction (chamfer_distance.cpp:237-244 ->

@@ -28,6 +28,7 @@ SIGNATURES = {
     "rslo_abi_version": (_i, []),
     "rslo_last_error": (C.c_char_p, []),
     "rslo_kernel_launch_count": (C.c_ulonglong, []),
+    "rslo_set_graph_capture_hint": (None, [_i]),
     "rslo_nn_workspace_bytes": (_sz, [_i, _i]),
     "rslo_nn_exact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "rslo_nn_brute": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp]),

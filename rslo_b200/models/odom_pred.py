@@ -281,8 +281,15 @@ class UNRResNetOdomPredEncDecSVDTempMask(nn.Module):
             flat.training = self.training
             bufs = {n: b.clone() for n, b in self.named_buffers()}
             sample = tuple(torch.randn_like(x).requires_grad_(x.requires_grad) for x in xs)
-            with torch.enable_grad():
-                g = torch.cuda.make_graphed_callables(flat, sample, allow_unused_input=True)
+            from .._lib import lib
+            # training graphs (forward + backward, ~880 nodes) are captured with programmatic dependent launch: +1 % on
+            # the train step; the forward-only eval graph measured 13 % SLOWER with it (316 vs 362 pairs/s), so not there
+            lib.rslo_set_graph_capture_hint(1 if self.training else 0)
+            try:
+                with torch.enable_grad():
+                    g = torch.cuda.make_graphed_callables(flat, sample, allow_unused_input=True)
+            finally:
+                lib.rslo_set_graph_capture_hint(0)
             with torch.no_grad():                      # capture warm-up ran BN on the random sample
                 for n, b in self.named_buffers():
                     b.copy_(bufs[n])
