@@ -93,6 +93,24 @@ def public_config(cfg, world=1, extra=None):
     return out
 
 
+def b200_config(cfg, world, ppg, reducer_bytes, train):
+    """`config` of the B200 arm's line; the reference arm carries the same keys (tests/test_cpu_host.py)"""
+    return public_config(cfg, world, {
+        "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
+              f"{max(2 * ppg, 4)} distinct pairs per rank",
+        "steps_in_flight": f"host at most {Runner.MAX_STEPS_IN_FLIGHT} steps ahead of the device (event wait)",
+        "grad_allreduce_bytes": reducer_bytes,
+        "optimizer": optimizer_note(train),
+        "note": "one process per GPU; value = pairs of all ranks / max-over-ranks device time of the timed steps"})
+
+
+def reference_config(cfg, cpu_budget_s):
+    return public_config(cfg, 1, {
+        "l2": "n/a (CPU arm)", "steps_in_flight": "n/a (CPU arm)", "grad_allreduce_bytes": 0,
+        "optimizer": optimizer_note(cfg["mode"] == "train"),
+        "note": f"CPU arm: rank 0 only, one replica's batch per step; steps/warm-up bounded by --cpu-budget-s {cpu_budget_s:.0f}"})
+
+
 def make_pairs(n, beams, n_az, first_seed):
     from rslo_b200.data import synthetic
     out = []
@@ -190,10 +208,7 @@ def reference_arm(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": done, "warmup": w_done, "ms_per_step": 1e3 * dt / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": public_config(cfg, 1, {
-                "l2": "n/a (CPU arm)", "steps_in_flight": "n/a (CPU arm)", "grad_allreduce_bytes": 0, "optimizer": optimizer_note(cfg["mode"] == "train"),
-                "note": "CPU arm: rank 0 only, one replica's batch per step; steps/warm-up bounded by "
-                        f"--cpu-budget-s {args.cpu_budget_s:.0f}"}),
+            "config": reference_config(cfg, args.cpu_budget_s),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -715,12 +730,7 @@ def main():
                 "ms_per_step_p90_max": [sorted(per)[int(0.9 * (len(per) - 1))], max(per)],
                 "host_enqueue_ms_per_step": host_ms, "host_phase_ms_per_step": host_phase, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": public_config(cfg, world, {
-                    "l2": "256 MB memset between steps (inside the timed region); inputs rotate over "
-                          f"{max(2 * ppg, 4)} distinct pairs per rank",
-                    "steps_in_flight": f"host at most {Runner.MAX_STEPS_IN_FLIGHT} steps ahead of the device (event wait)",
-                    "grad_allreduce_bytes": reducer_bytes,
-                    "optimizer": optimizer_note(run_train)}),
+                "config": b200_config(cfg, world, ppg, reducer_bytes, run_train),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "extra": extra}
         print(json.dumps(line), flush=True)

@@ -177,3 +177,24 @@ def test_pass_through_generator_packs_the_raw_scan_without_cuda():
     assert r["voxels"].shape == (500, 1, 7) and np.array_equal(r["voxels"][:, 0], pts)
     assert r["coordinates"].shape == (500, 3) and r["coordinates"].dtype == np.int32 and (r["coordinates"] == -1).all()
     assert r["num_points_per_voxel"].tolist() == [1] * 500
+
+
+def test_bench_arms_describe_the_same_config():
+    """Both arms of bench.py must name the same workload with the same keys (the driver compares their `config`)."""
+    import importlib
+    bench = importlib.import_module("bench")
+    for wl in ("train", "eval", "warm", "stress"):
+        cfg = bench.workload_config(wl)
+        ours = bench.b200_config(cfg, 1, cfg["pairs_per_gpu"], 0, cfg["mode"] == "train")
+        ref = bench.reference_config(cfg, 240.0)
+        assert set(ours) == set(ref)
+        for k in ("workload", "mode", "pairs_per_gpu", "global_pairs_per_step", "parallelism", "global_step", "optimizer"):
+            assert ours[k] == ref[k], k
+    assert bench.parse_args.__defaults__ is None        # defaults live in argparse: steps 100 / warm-up 20
+    import sys
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        a = bench.parse_args()
+    finally:
+        sys.argv = argv
+    assert a.gpus == 1 and a.steps >= 100 and a.warmup >= 20
