@@ -267,16 +267,17 @@ class ClockSampler:
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
-    best = None
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full captures (profiles/*_traffic.json): the capture
+    that averaged over the most launches of a step (ties: the latest), or None."""
+    best, best_n = None, -1
     pdir = os.path.join(ROOT, "profiles")
     if os.path.isdir(pdir):
         for fn in sorted(os.listdir(pdir)):
             if fn.endswith("_traffic.json"):
                 try:
                     d = json.load(open(os.path.join(pdir, fn)))
-                    if kernel in d:
-                        best = d[kernel]["dram_bytes_per_launch_avg"]
+                    if kernel in d and int(d[kernel].get("launches_captured", 0)) >= best_n:
+                        best, best_n = d[kernel]["dram_bytes_per_launch_avg"], int(d[kernel].get("launches_captured", 0))
                 except Exception:
                     pass
     return best
