@@ -27,6 +27,12 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.rslo_abi_version() >= 1
     from rslo_b200 import _lib
     assert set(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    # ... and nothing else: the trace / diagnostics builds (-DTC_TRACE: rslo_debug_*) must not be what ships
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "rslo_b200", "_C", "librslo_b200.so")],
+                         capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T rslo_" in ln}
+    assert exported == names, f"undeclared exports: {sorted(exported - names)}"
 
 
 def test_product_never_imports_oracle():
